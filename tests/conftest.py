@@ -1,0 +1,49 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+_DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, "float16": torch.float16}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """-> dict(meta, dtype, tensors..., sd=state dict with the dtypes the reference had)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dtype = _DT[str(z["dtype"])] if "dtype" in z.files else torch.float32
+    out = {"dtype": dtype, "meta": [int(v) for v in z["meta"]], "sd": {}}
+    for k in z.files:
+        if k in ("meta", "dtype"):
+            continue
+        t = torch.from_numpy(z[k])
+        if k.startswith("sd."):
+            key = k[3:]
+            fp32_param = any(s in key for s in ("A_logs", "Ds", "dt_projs_bias"))   # Inference.py:430-433
+            out["sd"][key] = t if fp32_param else t.to(dtype)
+        elif k.startswith("idx"):
+            out[k] = t
+        else:
+            out[k] = t.to(dtype)
+    return out
+
+
+LAYER_CASES = ["layer_ones_f32", "layer_rect_f32", "layer_zero_soft_f32", "layer_ones_bf16", "layer_rect_f16"]
