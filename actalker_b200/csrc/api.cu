@@ -1,0 +1,54 @@
+// C-ABI housekeeping: error text, version, A-structure probe, algorithmic-bytes helper.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace actk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Single CTA: every thread checks a strided slice, the block ANDs the verdicts and thread 0 publishes it.
+__global__ void __launch_bounds__(1024) a_structure_kernel(const float *__restrict__ A, int dim, int N, float rel_tol,
+                                                           int *flag) {
+  int ok = 1;
+  for (int i = threadIdx.x; i < dim * N; i += blockDim.x) {
+    const int d = i / N, n = i % N;
+    const float want = (float)(n + 1) * A[(size_t)d * N];
+    if (!(fabsf(A[i] - want) <= rel_tol * fabsf(want))) ok = 0;
+  }
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0) *flag = ok ? ACTK_A_POWER : ACTK_A_GENERAL;
+}
+
+}  // namespace actk
+
+using namespace actk;
+
+extern "C" int actk_abi_version(void) { return ACTK_ABI_VERSION; }
+extern "C" int actk_sm_arch(void) { return 100; }
+extern "C" const char *actk_last_error(void) { return g_err; }
+
+extern "C" int actk_a_structure(const float *A, int dim, int dstate, float rel_tol, int *flag_dev, void *stream) {
+  if (!A || !flag_dev) ACTK_FAIL(ACTK_ERR_BAD_ARG, "actk_a_structure: NULL pointer");
+  if (dim <= 0 || dstate <= 0) ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "actk_a_structure: dim=%d dstate=%d", dim, dstate);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  a_structure_kernel<<<1, 1024, 0, st>>>(A, dim, dstate, rel_tol, flag_dev);
+  ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
+}
+
+extern "C" long long actk_scan_algorithmic_bytes(int batch, int seqlen, int dim, int groups, int dstate, int elsize) {
+  // u, delta read + y written at (batch, dim, seqlen); B, C read at (batch, groups, dstate, seqlen);
+  // A, D, delta_bias (fp32) once.  SURVEY.md §8(d).
+  const long long act = (long long)batch * seqlen * (3LL * dim + 2LL * groups * dstate) * elsize;
+  const long long par = (long long)dim * (dstate + 2) * 4;
+  return act + par;
+}

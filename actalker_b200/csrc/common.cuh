@@ -1,0 +1,137 @@
+// Shared device helpers for the sm_100a kernels: dtype traits, packed fp32x2 math, MUFU wrappers,
+// mbarrier + bulk-async-copy (TMA) PTX.  No torch, no CUTLASS: plain CUDA + inline PTX.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/actalker_b200.h"
+
+namespace actk {
+
+constexpr int kN = ACTK_DSTATE;  // 16 states per channel
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ----------------------------------------------------------------------------- error plumbing
+void set_error(const char *fmt, ...);
+#define ACTK_FAIL(code, ...)  \
+  do {                        \
+    set_error(__VA_ARGS__);   \
+    return (code);            \
+  } while (0)
+#define ACTK_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) ACTK_FAIL(ACTK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ----------------------------------------------------------------------------- dtype traits
+template <typename T> struct IO;
+template <> struct IO<float> {
+  static __device__ __forceinline__ float ld(const float *p) { return *p; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }
+  static __device__ __forceinline__ void st(float *p, float v) { *p = v; }
+};
+template <> struct IO<__half> {
+  static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+  static __device__ __forceinline__ void st(__half *p, float v) { *p = __float2half_rn(v); }
+};
+template <> struct IO<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16 *p) {
+    return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t *>(p)) << 16);
+  }
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ----------------------------------------------------------------------------- MUFU wrappers
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// torch.nn.functional.softplus(x) with beta=1, threshold=20 (the rule selective_scan_fn applies when
+// delta_softplus=True): x > 20 ? x : log1p(exp(x)).  For small e = exp(x) the 1+e rounding of a plain
+// log(1+e) would cost relative accuracy, so the three-term series takes over below 2^-6.
+__device__ __forceinline__ float softplus20(float x) {
+  float e = ex2(x * kLog2e);
+  float big = lg2(1.0f + e) * kLn2;
+  float small = e * (1.0f + e * (-0.5f + e * 0.33333334f));
+  float r = e < 0.015625f ? small : big;
+  return x > 20.0f ? x : r;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + ex2(-x * kLog2e)); }
+
+// ----------------------------------------------------------------------------- packed fp32x2 (sm_100+)
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ----------------------------------------------------------------------------- mbarrier / TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk async copy (TMA unit, SASS UBLKCP); size % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace actk

@@ -1,0 +1,147 @@
+// Direction merge + branch sum + LayerNorm (C-ABI entry actk_merge_layernorm_fwd).
+//
+// Reference (src/models/base/mamba_layer.py): :1542-1547 y = y_fwd + flip(y_bwd) per branch; :1970/:1981 the
+// result overwrites the selected rows of the in_proj output, other rows keep in_proj's value; :1983 xz2 + xz1;
+// :1984 out_norm.  One warp per latent-token row; a row is read once with 128-bit loads, kept in registers for
+// the two-pass mean/variance, and written once.  Every intermediate the reference materialises as a `dtype`
+// tensor is rounded at the same point here.
+#include "common.cuh"
+
+namespace actk {
+
+struct MergeParams {
+  actk_merge_ln_args a;
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float (&v)[8]) {
+  if (sizeof(T) == 4) {
+    float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 w = *reinterpret_cast<const uint4 *>(p);
+    const T *e = reinterpret_cast<const T *>(&w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = IO<T>::ld(e + i);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *p, const float (&v)[8]) {
+  if (sizeof(T) == 4) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 w;
+    T *e = reinterpret_cast<T *>(&w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) IO<T>::st(e + i, v[i]);
+    *reinterpret_cast<uint4 *>(p) = w;
+  }
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ MergeParams P) {
+  const actk_merge_ln_args &a = P.a;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long rows = (long long)a.Bp * a.L;
+  if (row >= rows) return;
+  const int l = (int)(row % a.L);
+  const int D = a.D, nvec = D >> 3;
+  const size_t off = (size_t)row * D;
+  const size_t dir1 = (size_t)rows * D;   // ydir[1] - ydir[0]
+
+  float x[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float acc[8];
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        if (br >= a.n_branches) break;
+        float t[8];
+        if (a.selected[br][l]) {
+          float f[8], g[8];
+          const T *y0 = (const T *)a.ydir[br] + off + 8 * v;
+          load8(y0, f);
+          load8(y0 + dir1, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(f[e] + g[e]);
+        } else {
+          load8((const T *)a.xz[br] + off + 8 * v, t);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { float d = x[i][e] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / D + a.eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float g[8], bt[8], o[8];
+      load8((const T *)a.gamma + 8 * v, g);
+      load8((const T *)a.beta + 8 * v, bt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf((x[i][e] - mean) * rstd, g[e], bt[e]);
+      store8((T *)a.out + off + 8 * v, o);
+    }
+  }
+}
+
+template <typename T>
+static int launch_merge(const actk_merge_ln_args *a, cudaStream_t stream) {
+  MergeParams P;
+  P.a = *a;
+  const int vpl = ((a->D >> 3) + 31) / 32;
+  const long long rows = (long long)a->Bp * a->L;
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+  if (vpl <= 4) merge_ln_kernel<T, 4><<<grid, 128, 0, stream>>>(P);
+  else if (vpl <= 8) merge_ln_kernel<T, 8><<<grid, 128, 0, stream>>>(P);
+  else if (vpl <= 16) merge_ln_kernel<T, 16><<<grid, 128, 0, stream>>>(P);
+  else merge_ln_kernel<T, 32><<<grid, 128, 0, stream>>>(P);
+  ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
+}
+
+}  // namespace actk
+
+using namespace actk;
+
+extern "C" int actk_merge_layernorm_fwd(const actk_merge_ln_args *a, void *stream) {
+  if (!a) ACTK_FAIL(ACTK_ERR_BAD_ARG, "actk_merge_layernorm_fwd: args is NULL");
+  if (a->dtype < ACTK_F32 || a->dtype > ACTK_BF16) ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "merge_ln: dtype=%d", a->dtype);
+  if (a->n_branches < 1 || a->n_branches > 2) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: n_branches=%d", a->n_branches);
+  if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->D % 8 != 0 || a->D > 8192)
+    ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "merge_ln: Bp=%d L=%d D=%d (D must be a multiple of 8, <= 8192)", a->Bp, a->L, a->D);
+  if (!a->gamma || !a->beta || !a->out) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: gamma, beta and out are required");
+  for (int i = 0; i < a->n_branches; ++i) {
+    if (!a->xz[i] || !a->ydir[i] || !a->selected[i]) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: branch %d has a NULL pointer", i);
+    if ((reinterpret_cast<uintptr_t>(a->xz[i]) | reinterpret_cast<uintptr_t>(a->ydir[i])) & 15)
+      ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "merge_ln: branch %d pointer not aligned to 16 bytes", i);
+  }
+  if ((reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->gamma) | reinterpret_cast<uintptr_t>(a->beta)) & 15)
+    ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "merge_ln: out/gamma/beta not aligned to 16 bytes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case ACTK_F32: return launch_merge<float>(a, st);
+    case ACTK_F16: return launch_merge<__half>(a, st);
+    default: return launch_merge<__nv_bfloat16>(a, st);
+  }
+}

@@ -1,0 +1,286 @@
+"""Drop-in `SS2D_cond_v10` / `SS2D_Unit` running on the sm_100a kernels.
+
+Mirror of the reference's live masked Mamba control layer, src/models/base/mamba_layer.py:
+    SS2D_Unit      :1394-1553   (bidirectional K=2 selective-scan unit)
+    SS2D_cond_v10  :1902-1986   (audio + expression branches, mask gather/scatter, LayerNorm, out_proj)
+Same constructor arguments, same `forward(x, id_emb, conds, masks)`, same parameter names, shapes and dtypes
+(SURVEY.md Appendix C), so `unet.load_state_dict(strict=True)` (Inference.py:124-127) and the fp32 re-cast of
+`A_logs | Ds | dt_projs_bias` (Inference.py:430-433) keep working unchanged.
+
+What runs where
+    cuBLAS (via torch): in_proj1/2, id/audio/exp projections, x_proj, dt_proj, out_proj — dense GEMMs, the
+        same contractions and 16-bit rounding points as the reference's nn.Linear / einsum calls.
+    this repo's kernels (C-ABI, include/actalker_b200.h):
+        actk_masked_scan_fwd       gather -> tail concat -> both scan directions -> scatter   (:1963-1970, :1505-1548)
+        actk_merge_layernorm_fwd   direction sum, passthrough rows, branch sum, out_norm      (:1542-1547, :1983-1984)
+The mask -> index computation is the reference's own expression, cached per mask (mask.py).
+Forward only: inference runs under no_grad (pipeline ...two_ip.py:351); backward is not built.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .mask import MaskIndex, MaskIndexCache
+from .selective_scan_interface import _DTYPES, _ptr, _stream, a_kind_of
+
+__all__ = ["SS2D_Unit", "SS2D_cond_v10", "MAMBA_AVAILABLE"]
+
+try:
+    _lib.load()
+    MAMBA_AVAILABLE = True
+except _lib.LibraryMissing:
+    MAMBA_AVAILABLE = False
+
+_N = 16  # d_state compiled into the kernels
+
+# Optional kernel timing hook (bench.py): when set to a dict, every C-ABI launch is bracketed by CUDA events
+# on the launching stream and the (name, start, end) triples are appended to TIMING["events"].
+TIMING = None
+
+
+class _timed:
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.e.record(torch.cuda.current_stream(self.device))
+            TIMING.setdefault("events", []).append((self.name, self.s, self.e))
+        return False
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class SS2D_Unit(nn.Module):
+    """Parameters and initialisers of mamba_layer.py:1394-1502; forward == forward_core (:1505-1548)."""
+
+    def __init__(self, d_model, d_cond, cond_size=0, d_state=16, d_conv=3, expand=2, dt_rank="auto",
+                 dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 dropout=0.0, conv_bias=True, bias=False, device=None, dtype=None, size=8,
+                 scan_type="scan", num_direction=8, **kwargs):
+        super().__init__()
+        fk = {"device": device, "dtype": dtype}
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.d_cond = d_cond
+        self.num_direction = K = num_direction
+        self.scan_type = scan_type
+        c = self.dt_rank + 2 * d_state
+        self.x_proj_weight = nn.Parameter(torch.stack(
+            [nn.Linear(self.d_inner, c, bias=False, **fk).weight for _ in range(K)], dim=0))        # (K, R+2N, D)
+        dt_projs = [self.dt_init(self.dt_rank, self.d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor, **fk)
+                    for _ in range(K)]
+        self.dt_projs_weight = nn.Parameter(torch.stack([p.weight for p in dt_projs], dim=0))       # (K, D, R)
+        self.dt_projs_bias = nn.Parameter(torch.stack([p.bias for p in dt_projs], dim=0))           # (K, D)
+        self.A_logs = self.A_log_init(d_state, self.d_inner, copies=K, device=device)               # (K*D, N) fp32
+        self.Ds = self.D_init(self.d_inner, copies=K, device=device)                                # (K*D,)   fp32
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None   # constructed, never applied (as upstream)
+        self._derived = None
+        self._derived_key = None
+
+    # -- initialisers: the synthetic parameter distribution of the benchmarks (mamba_layer.py:1450-1502)
+    @staticmethod
+    def dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4, **fk):
+        proj = nn.Linear(dt_rank, d_inner, bias=True, **fk)
+        std = dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(proj.weight, -std, std)
+        else:
+            raise NotImplementedError
+        dt = torch.exp(torch.rand(d_inner, **fk) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min))
+        dt = dt.clamp(min=dt_init_floor)
+        with torch.no_grad():
+            proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))     # softplus^-1(dt)
+        return proj
+
+    @staticmethod
+    def A_log_init(d_state, d_inner, copies=1, device=None, merge=True):
+        a = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32, device=device)).repeat(d_inner, 1)
+        if copies > 1:
+            a = a.repeat(copies, 1) if merge else a[None].repeat(copies, 1, 1)
+        return nn.Parameter(a.contiguous())
+
+    @staticmethod
+    def D_init(d_inner, copies=1, device=None, merge=True):
+        d = torch.ones(d_inner * (copies if copies > 1 and merge else 1), dtype=torch.float32, device=device)
+        if copies > 1 and not merge:
+            d = d.view(1, -1).repeat(copies, 1)
+        return nn.Parameter(d)
+
+    # -- derived, kernel-friendly weights; rebuilt when a parameter is replaced or modified in place
+    def derived(self):
+        ps = (self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
+        key = tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in ps)
+        if self._derived is not None and key == self._derived_key:
+            return self._derived
+        K, D, R, N = self.num_direction, self.d_inner, self.dt_rank, self.d_state
+        if K != 2 or N != _N:
+            raise NotImplementedError(f"kernels are built for num_direction=2, d_state={_N} (the live layer); "
+                                      f"got K={K}, d_state={N}")
+        with torch.no_grad():
+            xw = _pad8(2 * K * N + K * R)
+            wx = self.x_proj_weight                                   # (K, R+2N, D)
+            w = wx.new_zeros(xw, D)
+            for k in range(K):
+                w[k * 2 * N:k * 2 * N + 2 * N] = wx[k, R:R + 2 * N]   # [B_k | C_k]
+                w[2 * K * N + k * R:2 * K * N + (k + 1) * R] = wx[k, :R]
+            wbd = wx.new_zeros(xw - 2 * K * N, K * D)                 # block-diagonal dt_proj, (K*R [+pad], K*D)
+            for k in range(K):
+                wbd[k * R:(k + 1) * R, k * D:(k + 1) * D] = self.dt_projs_weight[k].t()
+            A = (-torch.exp(self.A_logs.float())).contiguous()        # (K*D, N), as mamba_layer.py:1530
+            d = {"xw": xw, "w_xproj": w.contiguous(), "w_dt": wbd.contiguous(), "A": A,
+                 "Ds": self.Ds.float().contiguous().view(-1), "dt_bias": self.dt_projs_bias.float().contiguous().view(-1),
+                 "a_kind": a_kind_of(A) if A.is_cuda else _lib.ACTK_A_GENERAL}
+        self._derived, self._derived_key = d, key
+        return d
+
+    def forward_core(self, x: torch.Tensor):
+        """x: (B, D, L) -> (B, D, L).  Same contract as upstream; internally token-major."""
+        Bsz, D, L = x.shape
+        xt = x.permute(0, 2, 1)
+        if not xt.is_contiguous():
+            xt = xt.contiguous()
+        idx = torch.arange(L, dtype=torch.int32, device=x.device)
+        ydir = _scan_branches([self], [xt], [None], [idx], [L], Bsz, L)[0]      # (2, B, L, D)
+        return (ydir[0] + ydir[1]).permute(0, 2, 1)
+
+    def forward(self, input):
+        return self.forward_core(input)
+
+
+def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None):
+    """Shared launcher: x_proj / dt_proj GEMMs (cuBLAS) + one actk_masked_scan_fwd for all given branches.
+    xzs[i]: (Bp, L, D) contiguous; tails[i]: (Bp, n_tail, D) or None; idxs[i]: int32 (n_sel,).
+    Returns per-branch ydir tensors (2, Bp, L, D); rows of unselected tokens are uninitialised."""
+    lib = _lib.load()
+    x0 = xzs[0]
+    if not x0.is_cuda:
+        raise RuntimeError("actalker_b200 layers run on CUDA tensors only (no CPU path)")
+    if x0.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported activation dtype {x0.dtype}")
+    D = x0.shape[-1]
+    args = _lib.MaskedScanArgs()
+    args.n_branches, args.Bp, args.L, args.D, args.N = len(units), Bp, L, D, _N
+    args.dtype = _DTYPES[x0.dtype]
+    keep, outs = [], []
+    for i, unit in enumerate(units):
+        dv = unit.derived()
+        xz, tail, n_sel = xzs[i], tails[i], n_sels[i]
+        n_tail = 0 if tail is None else tail.shape[1]
+        ydir = torch.empty((2, Bp, L, D), dtype=xz.dtype, device=xz.device)
+        outs.append(ydir)
+        b = args.br[i]
+        b.n_sel, b.n_tail, b.a_kind = n_sel, n_tail, dv["a_kind"]
+        if n_sel == 0:
+            continue
+        xw = dv["xw"]
+        w_x = dv["w_xproj"].to(xz.dtype)
+        xdbl = F.linear(xz, w_x)                                           # (Bp, L, xw)
+        dtr = xdbl[..., 4 * _N:]
+        if n_sel != L:
+            dtr = dtr.index_select(1, idx64s[i] if idx64s is not None else idxs[i].long())
+        xdbl_tail = None
+        if n_tail:
+            xdbl_tail = F.linear(tail, w_x)                                # (Bp, n_tail, xw)
+            dtr = torch.cat([dtr, xdbl_tail[..., 4 * _N:]], dim=1)
+        delta = torch.matmul(dtr, dv["w_dt"].to(xz.dtype))                 # (Bp, Lp, 2D), sequence order
+        if i == 0:
+            args.xw = xw
+        elif args.xw != xw:
+            raise RuntimeError("branches disagree on the x_proj width")
+        b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
+        b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(dv["A"]), _ptr(dv["Ds"]), _ptr(dv["dt_bias"]), _ptr(ydir)
+        keep += [xdbl, xdbl_tail, delta, w_x]
+    if any(n > 0 for n in n_sels):
+        with torch.cuda.device(x0.device), _timed("masked_scan", x0.device):
+            _lib.check(lib.actk_masked_scan_fwd(ct.byref(args), _stream(x0)), "actk_masked_scan_fwd")
+    return outs
+
+
+class SS2D_cond_v10(nn.Module):
+    """mamba_layer.py:1902-1986, constructed exactly as TransformerSTmodel.py:3960-3974 does."""
+
+    def __init__(self, d_model, d_cond, cond_size=0, d_state=16, d_conv=3, expand=2, dt_rank="auto",
+                 dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 dropout=0.0, conv_bias=True, bias=False, device=None, dtype=None, size=8,
+                 scan_type="scan", num_direction=8, **kwargs):
+        fk = {"device": device, "dtype": dtype}
+        super().__init__()
+        unit_args = (d_model, d_cond, cond_size, d_state, d_conv, expand, dt_rank, dt_min, dt_max, dt_init,
+                     dt_scale, dt_init_floor, dropout, conv_bias, bias, device, dtype, size, scan_type, num_direction)
+        self.audio_unit = SS2D_Unit(*unit_args)
+        self.exp_unit = SS2D_Unit(*unit_args)
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.d_cond = d_cond
+        self.audio_proj = nn.Linear(d_cond, self.d_inner, bias=bias, **fk)
+        self.exp_proj = nn.Linear(d_cond, self.d_inner, bias=bias, **fk)
+        self.id_proj = nn.Linear(d_cond, self.d_inner, bias=bias, **fk)
+        self.in_proj1 = nn.Linear(d_model, self.d_inner, bias=bias, **fk)
+        self.in_proj2 = nn.Linear(d_model, self.d_inner, bias=bias, **fk)
+        self.act1 = nn.SiLU()
+        self.act2 = nn.SiLU()
+        self.num_direction = num_direction
+        self.out_norm = nn.LayerNorm(self.d_inner)
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **fk)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None   # never applied upstream either (:1952)
+        self.scan_type = scan_type
+        if scan_type != "sweep":
+            # upstream's HSCANS_dynamic('scan') raises for every L > 1 (mamba_layer.py:150-151); only 'sweep'
+            # (the identity order) is live (TransformerSTmodel.py:3969)
+            raise NotImplementedError("only scan_type='sweep' is live in the reference")
+        self.mask_cache = MaskIndexCache()
+
+    def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex):
+        """Both branches' gather -> bidirectional scan -> scatter, then merge + out_norm.  -> (Bp, L, D)."""
+        lib = _lib.load()
+        Bp, L, D = xz1.shape
+        ydirs = _scan_branches([self.audio_unit, self.exp_unit], [xz1, xz2], [tail1, tail2], [m1.idx, m2.idx],
+                               [m1.n_sel, m2.n_sel], Bp, L, idx64s=[m1.idx64, m2.idx64])
+        out = torch.empty_like(xz1)
+        a = _lib.MergeLnArgs()
+        for i, (xz, yd, m) in enumerate(((xz1, ydirs[0], m1), (xz2, ydirs[1], m2))):
+            a.xz[i], a.ydir[i], a.selected[i] = xz.data_ptr(), yd.data_ptr(), m.selected.data_ptr()
+        gamma, beta = self.out_norm.weight.to(xz1.dtype), self.out_norm.bias.to(xz1.dtype)
+        a.gamma, a.beta, a.out = _ptr(gamma), _ptr(beta), _ptr(out)
+        a.eps, a.n_branches, a.Bp, a.L, a.D, a.dtype = self.out_norm.eps, 2, Bp, L, D, _DTYPES[xz1.dtype]
+        with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
+            _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
+        return out
+
+    def forward(self, x, id_emb, conds, masks):
+        # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
+        # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("actalker_b200.SS2D_cond_v10 is forward-only (the reference's inference path, "
+                                      "pipeline ...two_ip.py:351); call it under torch.no_grad()")
+        Bp, L, _ = x.shape
+        audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
+        id_tok = self.act2(self.id_proj(id_emb))
+        xz1 = self.in_proj1(x)
+        xz2 = self.in_proj2(x)
+        m1 = self.mask_cache.get(masks[0], L)
+        m2 = self.mask_cache.get(masks[1], L)
+        tail1 = torch.cat([id_tok, self.act1(self.audio_proj(audio_cond))], dim=1)
+        tail2 = torch.cat([id_tok, self.act2(self.exp_proj(exp_cond))], dim=1)
+        y = self.scan_core(xz1.contiguous(), xz2.contiguous(), tail1.contiguous(), tail2.contiguous(), m1, m2)
+        return self.out_proj(y)

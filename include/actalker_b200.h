@@ -1,0 +1,165 @@
+/*
+ * actalker_b200 — C-ABI of the B200-native masked selective-scan path.
+ *
+ * Drop-in boundary for ONE hot path of qazi0/ACTalker: the masked selective-state-space
+ * control layer `SS2D_cond_v10` (reference: src/models/base/mamba_layer.py:1902-1986) and
+ * the operator it calls, `mamba_ssm.ops.selective_scan_interface.selective_scan_fn`
+ * (reference call site: src/models/base/mamba_layer.py:1532-1538).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless a
+ *     comment says "host"; the library allocates nothing and keeps no state between calls
+ *     (matches the reference's ownership rule: caller owns all tensors);
+ *   - every entry point enqueues on the given `cudaStream_t` (passed as void*) and returns
+ *     without synchronising; all functions are thread-safe (per-thread last-error string);
+ *   - return value: ACTK_OK or an actk_status; actk_last_error() gives the text;
+ *   - built for sm_100a only; calling on another device returns ACTK_ERR_CUDA.
+ *
+ * The library is loaded from Python with ctypes (actalker_b200/_lib.py); INTEGRATION.md
+ * shows the binding a maintainer of the reference would add.
+ */
+#ifndef ACTALKER_B200_H_
+#define ACTALKER_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACTK_ABI_VERSION 1
+#define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
+
+typedef enum {
+  ACTK_OK = 0,
+  ACTK_ERR_BAD_SHAPE = 1,   /* a size is non-positive / inconsistent                      */
+  ACTK_ERR_BAD_DTYPE = 2,   /* dtype enum not one of actk_dtype                            */
+  ACTK_ERR_BAD_ALIGN = 3,   /* a pointer or row pitch breaks the documented alignment      */
+  ACTK_ERR_BAD_ARG = 4,     /* null pointer where one is required, bad flag                */
+  ACTK_ERR_CUDA = 5,        /* a CUDA runtime call failed; text holds cudaGetErrorString   */
+  ACTK_ERR_UNSUPPORTED = 6  /* valid for mamba-ssm but outside this build (e.g. dstate>64) */
+} actk_status;
+
+typedef enum { ACTK_F32 = 0, ACTK_F16 = 1, ACTK_BF16 = 2 } actk_dtype;
+
+/* A-matrix structure hint for the scan kernels (see actk_a_structure). */
+typedef enum {
+  ACTK_A_GENERAL = 0,  /* arbitrary real A: one exp per (channel, state, step)                      */
+  ACTK_A_POWER = 1     /* A[d][n] == (n+1) * A[d][0] (the S4D-real init, mamba_layer.py:1476-1490):
+                          exp(dt*A[d][n]) = r^(n+1), one exp per (channel, step)                   */
+} actk_a_kind;
+
+int actk_abi_version(void);             /* == ACTK_ABI_VERSION                                   */
+int actk_sm_arch(void);                 /* 100: the only architecture in the fat binary          */
+const char *actk_last_error(void);      /* host string, valid until the next call on this thread */
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Operator contract — replaces mamba_ssm selective_scan_fn as called at
+ *     mamba_layer.py:1532-1538 (and the 9 non-live bindings listed in SURVEY.md §2).
+ *
+ *   u, delta, z, out : (batch, dim, seqlen), element stride 1 along seqlen, dtype `dtype`
+ *   A                : (dim, dstate) fp32, contiguous
+ *   B, C             : (batch, groups, dstate, seqlen), element stride 1 along seqlen, dtype `dtype`;
+ *                      channel d reads group d / (dim / groups)
+ *   D, delta_bias    : (dim) fp32 or NULL
+ *   z                : NULL, or gate: out *= silu(z)
+ *   last_state       : NULL, or (batch, dim, dstate) fp32 contiguous, receives h after the last step
+ *   all internal arithmetic fp32; result rounded once to `dtype`.
+ *   Strides are in ELEMENTS. dstate == 16 takes the tuned kernel; 1..64 a generic one.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *u, *delta, *B, *C, *z;
+  const float *A, *D, *delta_bias;
+  void *out;
+  float *last_state;
+  int batch, dim, groups, dstate, seqlen;
+  long long u_sb, u_sd, delta_sb, delta_sd, z_sb, z_sd, out_sb, out_sd; /* batch / dim strides     */
+  long long B_sb, B_sg, B_sn, C_sb, C_sg, C_sn;                          /* batch / group / state  */
+  int dtype;          /* actk_dtype                                                               */
+  int delta_softplus; /* 0/1: delta = x > 20 ? x : log1p(exp(x)) after the bias add               */
+  int a_kind;         /* actk_a_kind hint; ACTK_A_GENERAL is always valid                         */
+} actk_scan_args;
+
+int actk_selective_scan_fwd(const actk_scan_args *args, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) Fused masked bidirectional scan — the core of SS2D_cond_v10.forward for one or both
+ *     branches (mamba_layer.py:1963-1970, 1974-1981) with SS2D_Unit.forward_core
+ *     (mamba_layer.py:1505-1548) folded in: token gather through the mask index, the id/cond
+ *     tail tokens, both scan directions (the backward one by reversed addressing instead of a
+ *     flipped copy), dt-bias + softplus, D skip, and the scatter back to latent-token rows.
+ *     Token-major layouts (channels contiguous):
+ *
+ *   xz        : (Bp, L, D)        in_proj output; the scan input of sequence position p < n_sel is
+ *                                 row idx[p]
+ *   tail      : (Bp, n_tail, D)   id token followed by the projected condition tokens
+ *                                 (sequence positions n_sel .. n_sel+n_tail-1)
+ *   xdbl      : (Bp, L, xw)       x_proj output of the latent tokens; columns [0, 4*N) hold
+ *                                 [B_dir0 | C_dir0 | B_dir1 | C_dir1]; xw*elsize % 16 == 0
+ *   xdbl_tail : (Bp, n_tail, xw)  same for the tail tokens
+ *   delta     : (Bp, Lp, 2*D)     dt_proj output in SEQUENCE order, Lp = n_sel + n_tail;
+ *                                 columns [k*D, (k+1)*D) belong to direction k; position p holds the
+ *                                 token at position p for BOTH directions (direction 1 walks p downwards)
+ *   idx       : (n_sel) int32     ascending latent-token rows selected by the region mask
+ *   A         : (2*D, N) fp32     -exp(A_logs);  Dskip, dt_bias: (2*D) fp32
+ *   ydir      : (2, Bp, L, D)     per-direction scan output scattered to latent rows idx[p];
+ *                                 rows of unselected tokens are NOT written
+ *   D * elsize % 16 == 0 (D % 64 == 0 fills every CTA), N == 16, row pitches multiples of 16 bytes,
+ *   pointers 16-byte aligned.
+ *   A branch with n_sel == 0 is skipped (nothing is selected, nothing is written).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *xz, *tail, *xdbl, *xdbl_tail, *delta;
+  const int *idx;
+  const float *A, *Dskip, *dt_bias;
+  void *ydir;
+  int n_sel, n_tail;
+  int a_kind; /* actk_a_kind */
+} actk_branch_args;
+
+typedef struct {
+  actk_branch_args br[2];
+  int n_branches; /* 1 or 2 */
+  int Bp, L, D, N, xw;
+  int dtype; /* actk_dtype of xz/tail/xdbl/delta/ydir */
+} actk_masked_scan_args;
+
+int actk_masked_scan_fwd(const actk_masked_scan_args *args, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Direction merge + branch sum + LayerNorm — mamba_layer.py:1542-1547 (y_fwd + flip(y_bwd)),
+ *     :1970/:1981 (scatter over the in_proj output) and :1983-1984 (xz2 + xz1, out_norm).
+ *     For every latent row r and branch i:
+ *         t_i = selected_i[r] ? round(round(ydir_i[0][r]) + round(ydir_i[1][r])) : xz_i[r]
+ *     out[r] = LayerNorm_D(round(t_1 + t_0)) * gamma + beta      (statistics in fp32)
+ *     The rounding points are the reference's (each scan result, each sum is a `dtype` tensor).
+ *   xz_i : (Bp, L, D); ydir_i : (2, Bp, L, D); selected_i : (L) uint8; gamma, beta : (D) `dtype`
+ *   out  : (Bp, L, D).  D % 8 == 0, D <= 8192.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *xz[2];
+  const void *ydir[2];
+  const unsigned char *selected[2];
+  const void *gamma, *beta;
+  void *out;
+  float eps;
+  int n_branches;
+  int Bp, L, D;
+  int dtype;
+} actk_merge_ln_args;
+
+int actk_merge_layernorm_fwd(const actk_merge_ln_args *args, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) A-structure probe.  Writes *flag_dev = ACTK_A_POWER if |A[d][n] - (n+1)*A[d][0]| <=
+ *     rel_tol * |(n+1)*A[d][0]| for every d, n, else ACTK_A_GENERAL.  Run once per weight load
+ *     (the Python layer caches the answer per parameter version).
+ * ------------------------------------------------------------------------------------------- */
+int actk_a_structure(const float *A, int dim, int dstate, float rel_tol, int *flag_dev, void *stream);
+
+/* Bytes of HBM the two scan entry points must move for given sizes (the "algorithmic bytes"
+ * Q of BASELINE.md §3 / SURVEY.md §8d); host-only helper used by bench.py and tests. */
+long long actk_scan_algorithmic_bytes(int batch, int seqlen, int dim, int groups, int dstate, int elsize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACTALKER_B200_H_ */

@@ -1,0 +1,114 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/actalker_b200.h
+declares, mirrors the header's structs, and rejects bad arguments before touching a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from actalker_b200 import _lib
+
+
+def header_text():
+    with open(os.path.join(ROOT, "include", "actalker_b200.h")) as f:
+        return f.read()
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    text = re.sub(r"/\*.*?\*/", "", header_text(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(actk_[a-z0-9_]+)\s*\(", text)))
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.actk_abi_version() == _lib.ABI_VERSION == int(re.search(r"ACTK_ABI_VERSION (\d+)", text).group(1))
+    assert lib.actk_sm_arch() == 100
+
+
+def test_no_torch_types_in_the_boundary():
+    text = header_text()
+    assert "torch" not in text.lower().replace("pytorch", "") and "at::" not in text and "#include <torch" not in text
+
+
+def test_algorithmic_bytes_matches_survey_figures():
+    lib = _lib.load()
+    q = lambda b, l: lib.actk_scan_algorithmic_bytes(b, l, 1280, 2, 16, 2)
+    assert abs((q(25, 5217) + q(25, 5186)) / 1e9 - 2.031) < 1e-3
+    q1 = lambda l: lib.actk_scan_algorithmic_bytes(14, l, 1280, 2, 16, 4)
+    assert abs((q1(1057) + q1(1026)) / 1e9 - 0.456) < 1e-3                # config 1 (fp32)
+
+
+def _status(name):
+    return {v: k for k, v in _lib.STATUS_NAMES.items()}[name]
+
+
+def test_argument_validation_happens_before_any_launch():
+    lib = _lib.load()
+    assert lib.actk_selective_scan_fwd(None, None) == _status("ACTK_ERR_BAD_ARG")
+    assert b"NULL" in lib.actk_last_error()
+    a = _lib.ScanArgs()
+    a.dtype = 7
+    assert lib.actk_selective_scan_fwd(C.byref(a), None) == _status("ACTK_ERR_BAD_DTYPE")
+    a.dtype = _lib.ACTK_BF16
+    assert lib.actk_selective_scan_fwd(C.byref(a), None) == _status("ACTK_ERR_BAD_SHAPE")
+    a.batch, a.dim, a.groups, a.dstate, a.seqlen = 1, 6, 4, 16, 8
+    assert lib.actk_selective_scan_fwd(C.byref(a), None) == _status("ACTK_ERR_BAD_SHAPE")   # 6 % 4
+    a.groups, a.dstate = 2, 128
+    assert lib.actk_selective_scan_fwd(C.byref(a), None) == _status("ACTK_ERR_UNSUPPORTED")
+    a.dstate = 16
+    assert lib.actk_selective_scan_fwd(C.byref(a), None) == _status("ACTK_ERR_BAD_ARG")     # null tensors
+
+    m = _lib.MaskedScanArgs()
+    m.dtype, m.n_branches, m.N, m.Bp, m.L, m.D, m.xw = _lib.ACTK_BF16, 2, 16, 1, 64, 100, 104
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_SHAPE")       # 200-byte rows
+    assert b"multiple of 8" in lib.actk_last_error()
+    m.D, m.xw = 128, 100
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_ALIGN")       # 200-byte pitch
+    m.xw, m.N = 104, 8
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_UNSUPPORTED")
+    m.N = 16
+    m.br[0].n_sel = 65
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_SHAPE")       # n_sel > L
+    m.br[0].n_sel = 4
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_ARG")         # null tensors
+
+    g = _lib.MergeLnArgs()
+    g.dtype, g.n_branches, g.Bp, g.L, g.D = _lib.ACTK_F16, 2, 1, 4, 12
+    assert lib.actk_merge_layernorm_fwd(C.byref(g), None) == _status("ACTK_ERR_BAD_SHAPE")   # D % 8
+    assert lib.actk_a_structure(None, 4, 16, 1e-6, None, None) == _status("ACTK_ERR_BAD_ARG")
+
+
+def test_check_maps_status_to_reference_exceptions():
+    lib = _lib.load()
+    a = _lib.ScanArgs()
+    a.dtype, a.batch, a.dim, a.groups, a.dstate, a.seqlen = 0, 1, 4, 1, 200, 4
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.actk_selective_scan_fwd(C.byref(a), None), "scan")
+    a.dstate = 16
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.actk_selective_scan_fwd(C.byref(a), None), "scan")
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "actalker_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_cpu_tensors_are_refused_loudly():
+    import torch
+    from actalker_b200 import SS2D_cond_v10, selective_scan_fn
+    u = torch.randn(1, 4, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        selective_scan_fn(u, u, -torch.ones(4, 16), torch.randn(1, 1, 16, 8), torch.randn(1, 1, 16, 8))
+    layer = SS2D_cond_v10(d_model=32, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=8,
+                          scan_type="sweep", num_direction=2).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.randn(1, 64, 32), torch.randn(1, 1, 64), torch.randn(1, 33, 64),
+              [torch.ones(1, 1, 64, 64), torch.ones(1, 1, 64, 64)])

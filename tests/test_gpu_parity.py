@@ -1,0 +1,258 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Tolerances (stated per dtype):
+  fp32 I/O : rtol 2e-4, atol 2e-5 against the oracle evaluated in float64 (MUFU ex2/lg2 are ~2^-22 accurate
+             and the recurrence compounds them);
+  bf16 I/O : rtol 1.6e-2, atol 1e-2 against the fp32 oracle on the same bf16 inputs (one output rounding, 2^-8);
+  fp16 I/O : rtol 2e-3, atol 2e-3.
+Index lists and everything integer are compared with torch.equal.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import LAYER_CASES, load_golden
+from oracle import SS2D_Unit_ref, SS2D_cond_v10_ref, mask_to_index as oracle_mask_to_index, selective_scan_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: (2e-4, 2e-5), torch.bfloat16: (1.6e-2, 1e-2), torch.float16: (2e-3, 2e-3)}
+LAYER_TOL = {torch.float32: (1e-3, 1e-4), torch.bfloat16: (3e-2, 3e-2), torch.float16: (5e-3, 5e-3)}
+
+
+def close(got, want, dtype, tol=TOL, what=""):
+    rtol, atol = tol[dtype]
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    err = (got - want).abs()
+    bound = atol + rtol * want.abs()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    worst = (err - bound).max().item()
+    assert worst <= 0, f"{what}: max abs err {err.max().item():.3e}, worst excess over tol {worst:.3e}"
+
+
+def scan_inputs(batch, dim, L, G, dtype, seed=0, N=16, structured=False, bias_shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(batch, dim, L, generator=g).to(dtype)
+    delta = (torch.randn(batch, dim, L, generator=g) + bias_shift).to(dtype)
+    A_log = torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(dim, 1)
+    if not structured:
+        A_log = A_log + 0.5 * torch.randn(dim, N, generator=g)
+    A = -torch.exp(A_log)
+    B = torch.randn(batch, G, N, L, generator=g).to(dtype)
+    C = torch.randn(batch, G, N, L, generator=g).to(dtype)
+    D = 1.0 + 0.2 * torch.randn(dim, generator=g)
+    bias = torch.randn(dim, generator=g) - 2.0
+    z = torch.randn(batch, dim, L, generator=g).to(dtype)
+    return u, delta, A, B, C, D, bias, z
+
+
+def run_fn(args, dev="cuda", **kw):
+    from actalker_b200 import selective_scan_fn
+    u, delta, A, B, C, D, bias, z = [t.to(dev) for t in args]
+    use_z = kw.pop("use_z", False)
+    use_D = kw.pop("use_D", True)
+    use_bias = kw.pop("use_bias", True)
+    return selective_scan_fn(u, delta, A, B, C, D if use_D else None, z if use_z else None,
+                             bias if use_bias else None, **kw)
+
+
+def run_ref(args, dtype, **kw):
+    u, delta, A, B, C, D, bias, z = args
+    use_z = kw.pop("use_z", False)
+    use_D = kw.pop("use_D", True)
+    use_bias = kw.pop("use_bias", True)
+    kw.pop("a_kind", None)
+    cd = torch.float64 if dtype == torch.float32 else torch.float32
+    return selective_scan_ref(u, delta, A, B, C, D if use_D else None, z if use_z else None,
+                              bias if use_bias else None, compute_dtype=cd, **kw)
+
+
+# ------------------------------------------------------------------------------------------ operator seam
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 128, 77, 2), (1, 100, 33, 2), (3, 64, 1, 1), (2, 192, 160, 3), (1, 8, 31, 4)])
+def test_selective_scan_fn_matches_oracle(dtype, shape):
+    batch, dim, L, G = shape
+    args = scan_inputs(batch, dim, L, G, dtype, seed=L)
+    got = run_fn(args, delta_softplus=True)
+    assert got.dtype == dtype and got.shape == (batch, dim, L)
+    close(got, run_ref(args, dtype, delta_softplus=True), dtype, what=f"scan {shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("opts", [dict(use_z=True, delta_softplus=True), dict(use_D=False, delta_softplus=True),
+                                  dict(use_bias=False, delta_softplus=True),
+                                  dict(use_z=True, use_D=False, use_bias=False, delta_softplus=True)])
+def test_selective_scan_fn_optional_arguments(dtype, opts):
+    args = scan_inputs(2, 96, 70, 2, dtype, seed=5)
+    close(run_fn(args, **dict(opts)), run_ref(args, dtype, **dict(opts)), dtype, what=str(opts))
+
+
+def test_selective_scan_fn_without_softplus_and_last_state():
+    args = list(scan_inputs(2, 64, 45, 2, torch.float32, seed=9))
+    args[1] = args[1].abs() * 0.1            # raw positive delta, as callers without softplus must provide
+    got, last = run_fn(args, delta_softplus=False, return_last_state=True)
+    want, want_last = run_ref(args, torch.float32, delta_softplus=False, return_last_state=True)
+    close(got, want, torch.float32, what="no softplus")
+    close(last, want_last, torch.float32, what="last state")
+    assert last.dtype == torch.float32 and last.shape == (2, 64, 16)
+
+
+@pytest.mark.parametrize("L", [2047, 2048, 2049, 5217])
+def test_selective_scan_fn_long_sequences(L):
+    args = scan_inputs(1, 64, L, 2, torch.float32, seed=L)
+    close(run_fn(args, delta_softplus=True), run_ref(args, torch.float32, delta_softplus=True), torch.float32,
+          what=f"L={L}")
+
+
+def test_selective_scan_fn_softplus_threshold_region():
+    args = list(scan_inputs(1, 64, 40, 1, torch.float32, seed=2))
+    args[1] = torch.linspace(-30.0, 30.0, 40).repeat(1, 64, 1) + 0.25 * args[1]   # sweeps across 20 and far below
+    args[6] = torch.zeros(64)
+    close(run_fn(args, delta_softplus=True), run_ref(args, torch.float32, delta_softplus=True), torch.float32,
+          what="softplus sweep")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_power_path_equals_general_path_and_oracle(dtype):
+    from actalker_b200 import a_kind_of, _lib
+    args = scan_inputs(2, 128, 300, 2, dtype, seed=11, structured=True)
+    assert a_kind_of(args[2].cuda()) == _lib.ACTK_A_POWER
+    assert a_kind_of(scan_inputs(1, 64, 4, 1, dtype, seed=1)[2].cuda()) == _lib.ACTK_A_GENERAL
+    want = run_ref(args, dtype, delta_softplus=True)
+    for kind in ("general", "power", "auto"):
+        close(run_fn(args, delta_softplus=True, a_kind=kind), want, dtype, what=kind)
+
+
+@pytest.mark.parametrize("N", [1, 8, 24, 64])
+def test_generic_dstate_kernel(N):
+    args = scan_inputs(2, 40, 50, 2, torch.float32, seed=N, N=N)
+    close(run_fn(args, delta_softplus=True, use_z=True), run_ref(args, torch.float32, delta_softplus=True, use_z=True),
+          torch.float32, what=f"dstate={N}")
+
+
+def test_strided_views_are_accepted_like_upstream():
+    args = list(scan_inputs(2, 64, 50, 2, torch.bfloat16, seed=4))
+    big = torch.randn(2, 50, 64).to(torch.bfloat16)
+    args[0] = big.permute(0, 2, 1)                       # last stride != 1 -> made contiguous, as mamba-ssm does
+    xdbl = torch.randn(2, 2, 40, 50).to(torch.bfloat16)
+    args[3], args[4] = xdbl[:, :, 4:20], xdbl[:, :, 20:36]   # split views with a larger group stride
+    close(run_fn(args, delta_softplus=True), run_ref(args, torch.bfloat16, delta_softplus=True), torch.bfloat16,
+          what="strided")
+
+
+# ------------------------------------------------------------------------------------------ mask indexing
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_mask_index_bit_exact(dtype):
+    from actalker_b200 import mask_to_index
+    from actalker_b200.mask import MaskIndexCache
+    masks = {"ones": torch.ones(1, 1, 576, 576), "zeros": torch.zeros(1, 1, 576, 576)}
+    rect = torch.zeros(1, 1, 576, 576)
+    rect[:, :, 300:480, 180:400] = 1.0
+    masks["rect"] = rect
+    k = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0]) / 16.0
+    masks["soft"] = F.conv2d(rect, (k[:, None] * k[None, :])[None, None], padding=2)
+    cache = MaskIndexCache()
+    for name, m in masks.items():
+        m = m.to(dtype)
+        for L in (5184, 1296, 324):
+            want = oracle_mask_to_index(m, L)
+            got = mask_to_index(m.cuda(), L)
+            assert torch.equal(got.cpu(), want), (name, L)
+            e = cache.get(m.cuda(), L)
+            assert e.n_sel == want.numel() and torch.equal(e.idx.cpu().long(), want)
+            assert torch.equal(e.selected.cpu().nonzero().view(-1), want)
+    misses = cache.misses
+    cache.get(m.cuda(), 324)          # different storage -> miss; same tensor -> hit
+    mg = m.cuda()
+    cache.get(mg, 324); before = cache.misses; cache.get(mg, 324)
+    assert cache.misses == before and before > misses
+
+
+# ------------------------------------------------------------------------------------------ module seam
+def build_pair(g, device="cuda"):
+    from actalker_b200 import SS2D_cond_v10
+    d_model, d_cond, side, _ = g["meta"]
+    kw = dict(d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16, size=side,
+              scan_type="sweep", num_direction=2)
+    ours = SS2D_cond_v10(**kw).eval()
+    if g["dtype"] != torch.float32:
+        ours = ours.to(g["dtype"])
+    ours.load_state_dict(g["sd"], strict=True)       # same keys / shapes as the reference (Appendix C)
+    ours = ours.to(device)
+    for name, p in ours.named_parameters():          # Inference.py:430-433
+        if any(s in name for s in ("A_logs", "Ds", "dt_projs_bias")):
+            p.data = p.data.float()
+    return ours
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layer_matches_reference_golden(case):
+    g = load_golden(case)
+    layer = build_pair(g)
+    dev = "cuda"
+    with torch.no_grad():
+        y = layer(g["x"].to(dev), g["id_emb"].to(dev), g["conds"].to(dev), [g["mask0"].to(dev), g["mask1"].to(dev)])
+    assert y.dtype == g["dtype"] and y.shape == g["y"].shape
+    L = g["x"].shape[1]
+    assert torch.equal(layer.mask_cache.get(g["mask0"].to(dev), L).idx64.cpu(), g["idx0"])
+    assert torch.equal(layer.mask_cache.get(g["mask1"].to(dev), L).idx64.cpu(), g["idx1"])
+    close(y, g["y"], g["dtype"], tol=LAYER_TOL, what=case)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cfg", [(64, 128, 12, 3, "rect"), (320, 1024, 16, 2, "ones"), (96, 64, 10, 2, "split")])
+def test_layer_matches_oracle_on_seeded_inputs(dtype, cfg):
+    from actalker_b200 import SS2D_cond_v10
+    d_model, d_cond, side, batch, mkind = cfg
+    torch.manual_seed(72589 + d_model)
+    kw = dict(d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16, size=side,
+              scan_type="sweep", num_direction=2)
+    ref = SS2D_cond_v10_ref(**kw).eval()
+    with torch.no_grad():
+        for unit in (ref.audio_unit, ref.exp_unit):
+            unit.A_logs.add_(0.5 * torch.randn_like(unit.A_logs))
+            unit.Ds.copy_(1.0 + 0.2 * torch.randn_like(unit.Ds))
+    ours = SS2D_cond_v10(**kw).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    if dtype != torch.float32:
+        ref, ours = ref.to(dtype), ours.to(dtype)
+        for m in (ref, ours):
+            for name, p in m.named_parameters():
+                if any(s in name for s in ("A_logs", "Ds", "dt_projs_bias")):
+                    p.data = p.data.float()
+    ours = ours.cuda()
+    L, px = side * side, side * 8
+    x = torch.randn(batch, L, d_model).to(dtype)
+    id_emb = torch.randn(batch, 1, d_cond).to(dtype)
+    conds = torch.randn(batch, 33, d_cond).to(dtype)
+    ones = torch.ones(1, 1, px, px)
+    top = torch.zeros(1, 1, px, px); top[:, :, : px // 2] = 1
+    bot = torch.zeros(1, 1, px, px); bot[:, :, px // 2:, px // 4: 3 * px // 4] = 1
+    masks = {"ones": [ones, ones], "rect": [bot, ones], "split": [bot, top]}[mkind]
+    masks = [m.to(dtype) for m in masks]
+    with torch.no_grad():
+        want = ref(x.clone(), id_emb, conds, masks)
+        got = ours(x.cuda(), id_emb.cuda(), conds.cuda(), [m.cuda() for m in masks])
+    close(got, want, dtype, tol=LAYER_TOL, what=f"{cfg} {dtype}")
+
+
+def test_unit_matches_reference_golden():
+    from actalker_b200 import SS2D_Unit
+    g = load_golden("unit_f32")
+    d_model, L, batch = g["meta"]
+    unit = SS2D_Unit(d_model, 64, 32, 16, size=8, scan_type="sweep", num_direction=2).eval()
+    unit.load_state_dict(g["sd"], strict=True)
+    unit = unit.cuda()
+    with torch.no_grad():
+        y = unit(g["x"].cuda())
+    close(y, g["y"], torch.float32, tol=LAYER_TOL, what="unit")
+
+
+def test_layer_is_forward_only_and_says_so():
+    from actalker_b200 import SS2D_cond_v10
+    layer = SS2D_cond_v10(d_model=32, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=8,
+                          scan_type="sweep", num_direction=2).cuda()
+    ones = torch.ones(1, 1, 64, 64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        layer(torch.randn(1, 64, 32, device="cuda"), torch.randn(1, 1, 64, device="cuda"),
+              torch.randn(1, 33, 64, device="cuda"), [ones, ones])
