@@ -20,7 +20,7 @@ namespace actk {
 
 constexpr int kCh = 64;      // channels per CTA
 constexpr int kT = 16;       // time steps per staged tile
-constexpr int kStages = 3;   // ring depth
+constexpr int kStages = 4;   // ring depth
 constexpr int kThreads = kCh + 32;
 
 template <typename T>
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads) masked_scan_kernel(const __grid_cons
   const int b = blockIdx.y;
   const int bi = P.first_branch + (blockIdx.z >> 1);
   const int k = blockIdx.z & 1;
-  const BranchDev<T> &br = P.br[bi];
+  const BranchDev<T> br = P.br[bi];   // by value: keeps the fields in registers instead of indexed constant loads
   const int n_sel = br.n_sel, n_tail = br.n_tail;
   const int Lp = n_sel + n_tail;
   const int D = P.D, L = P.L;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) masked_scan_kernel(const __grid_cons
     const int pre = min(kStages - 1, ntiles);
     for (int t = 0; t < pre; ++t) issue(t);
     for (int t = 0; t < ntiles; ++t) {
-      if (t + kStages - 1 < ntiles) issue(t + kStages - 1);
+      // publish tile t first (it landed while the compute warps were busy with earlier tiles) ...
       const int s = t % kStages;
       const uint32_t ph = (t / kStages) & 1;
       mbar_wait(&full_bar[s], ph);
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(kThreads) masked_scan_kernel(const __grid_cons
         }
       }
       mbar_arrive(&ready_bar[s]);
+      // ... then refill the stage the compute warps released last (blocks until they are done with tile t-1)
+      if (t + kStages - 1 < ntiles) issue(t + kStages - 1);
     }
   } else {
     // ------------------------------------------------------------------ compute warps: one channel per thread

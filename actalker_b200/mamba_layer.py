@@ -202,10 +202,9 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
             xdbl_tail = F.linear(tail, w_x)                                # (Bp, n_tail, xw)
             dtr = torch.cat([dtr, xdbl_tail[..., 4 * _N:]], dim=1)
         delta = torch.matmul(dtr, dv["w_dt"].to(xz.dtype))                 # (Bp, Lp, 2D), sequence order
-        if i == 0:
-            args.xw = xw
-        elif args.xw != xw:
+        if args.xw not in (0, xw):
             raise RuntimeError("branches disagree on the x_proj width")
+        args.xw = xw
         b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
         b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(dv["A"]), _ptr(dv["Ds"]), _ptr(dv["dt_bias"]), _ptr(ydir)
         keep += [xdbl, xdbl_tail, delta, w_x]

@@ -49,13 +49,20 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-
-    def run(self):
+        self.nv = self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
+            nv, h = self.nv, self.h
             names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
@@ -64,8 +71,8 @@ class ClockSampler(threading.Thread):
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.reasons |= {n for bit, n in names.items() if r & bit}
-                time.sleep(0.02)
-        except Exception as e:  # NVML missing: report that instead of inventing clocks
+                time.sleep(0.002)
+        except Exception as e:
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def summary(self):
@@ -83,10 +90,15 @@ def make_layer(cls, d_model, dtype, params, device, seed):
                 unit.A_logs.add_(0.5 * torch.randn_like(unit.A_logs))
                 unit.Ds.copy_(1.0 + 0.2 * torch.randn_like(unit.Ds))
     if dtype != torch.float32:
+        keep = {n: p.data.clone() for n, p in layer.named_parameters()
+                if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias"))}
         layer = layer.to(dtype)
-        for name, p in layer.named_parameters():     # Inference.py:430-433
-            if any(s in name for s in ("A_logs", "Ds", "dt_projs_bias")):
-                p.data = p.data.float()
+        for name, p in layer.named_parameters():
+            if name in keep:
+                # "init"/"trained": the reference's own flow — the whole UNet is cast to 16 bit (Inference.py:200-202)
+                # and these three are cast BACK to fp32 (:430-433), so they hold 16-bit-rounded values.
+                # "s4d": they never leave fp32, so A keeps the exact S4D-real structure A[d][n] = -(n+1).
+                p.data = keep[name] if params == "s4d" else p.data.float()
     return layer.to(device)
 
 
@@ -264,7 +276,7 @@ def main():
     ap.add_argument("--cfg", type=int, default=1)
     ap.add_argument("--d-model", dest="d_model", type=int, default=320)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
-    ap.add_argument("--params", default="init", choices=["init", "trained"])
+    ap.add_argument("--params", default="init", choices=["init", "trained", "s4d"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

@@ -90,8 +90,8 @@ def test_selective_scan_fn_optional_arguments(dtype, opts):
 def test_selective_scan_fn_without_softplus_and_last_state():
     args = list(scan_inputs(2, 64, 45, 2, torch.float32, seed=9))
     args[1] = args[1].abs() * 0.1            # raw positive delta, as callers without softplus must provide
-    got, last = run_fn(args, delta_softplus=False, return_last_state=True)
-    want, want_last = run_ref(args, torch.float32, delta_softplus=False, return_last_state=True)
+    got, last = run_fn(args, delta_softplus=False, return_last_state=True, use_bias=False)
+    want, want_last = run_ref(args, torch.float32, delta_softplus=False, return_last_state=True, use_bias=False)
     close(got, want, torch.float32, what="no softplus")
     close(last, want_last, torch.float32, what="last state")
     assert last.dtype == torch.float32 and last.shape == (2, 64, 16)
