@@ -112,17 +112,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// The wait sleeps in hardware until the phase completes or the hint expires; the default hint is so short
+// that an idle producer warp re-polls every ~45 cycles and takes issue slots from the compute warps.
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(kSuspendHintNs)
       : "memory");
 }
 // global -> shared bulk async copy (TMA unit, SASS UBLKCP); size % 16 == 0, both addresses 16-byte aligned.
@@ -132,6 +135,40 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 3-D tiled TMA load (SASS UTMALDG): box described by the tensor map, coordinates innermost first.
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+// 3-D tiled TMA store (SASS UTMASTG), tracked by the bulk async-group of the issuing thread.
+__device__ __forceinline__ void tma_store_3d(const void *tmap, int c0, int c1, int c2, const void *src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap),
+               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src_smem))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmap_prefetch(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// 16-byte Ampere-style async copy (SASS LDGSTS) for ragged gather tiles, completing on an mbarrier.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace actk

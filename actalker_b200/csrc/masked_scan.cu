@@ -1,7 +1,7 @@
 // Fused masked bidirectional selective scan (C-ABI entry actk_masked_scan_fwd).
 //
 // Replaces, for one call of SS2D_cond_v10.forward (reference src/models/base/mamba_layer.py):
-//   :1963/:1974  gather of the mask-selected tokens           -> rows are fetched through idx[] by the TMA producer
+//   :1963/:1974  gather of the mask-selected tokens           -> tiles are fetched through idx[] (TMA boxes / cp.async rows)
 //   :1965-1967   cat([selected, id, cond])                    -> tail rows come from a second base pointer
 //   :1508-1519   HSCANS_dynamic identity encode + flip + cat  -> direction 1 walks the same rows downwards
 //   :1532-1538   selective_scan_fn (bias, softplus, scan, D)  -> ChannelScan::step, fp32 state in registers
@@ -9,19 +9,28 @@
 // The direction sum (:1542-1547) and branch sum (:1983) need the reference's rounding points and are done by
 // actk_merge_layernorm_fwd, which reads the two per-direction outputs written here.
 //
-// Work decomposition (B200: 148 SMs): one CTA = 64 channels x one (batch, branch, direction); 2 compute warps
-// (one thread per channel, 16 states in registers) + 1 producer warp.  The producer warp stages kT-step tiles
-// of u / delta / B|C rows into a kStages-deep shared-memory ring with bulk async copies (TMA, SASS UBLKCP)
-// completing on mbarriers, converts the B|C rows to fp32 once per CTA, and publishes the scatter rows.
-// Config 2 (B'=25, D=640, 2 branches x 2 directions) gives 1000 CTAs = 6.8 per SM, all co-resident.
+// Work decomposition (B200, 148 SMs): one CTA = 64 channels x one (batch, branch, direction), one thread per
+// channel with its 16 states in registers; config 2 (B'=25, D=640) gives 1000 CTAs = 6.8 per SM, all resident.
+// Time is cut into 16-step tiles staged through a shared-memory ring:
+//   * FAST tiles (16 selected tokens whose latent rows are consecutive — every tile under the all-ones masks
+//     the shipped pipeline feeds, Inference.py:545-546): one elected thread issues three 3-D tensor-map TMA
+//     loads (u, delta, B|C boxes; SASS UTMALDG) completing on the stage's mbarrier, and the y tile goes back
+//     with one TMA store (UTMASTG);
+//   * RAGGED tiles (mask edges, the id/cond tail, partial last tile, D % 64 != 0): all threads gather 16-byte
+//     pieces with cp.async (LDGSTS) arriving on the same mbarrier, and store y rows with 128-bit STG.
+// One __syncthreads per tile publishes the fp32-widened B|C rows and releases the oldest stage for refill; there
+// is no producer warp and nothing spins.
+#include <cuda.h>
+#include <string.h>
+
 #include "scan_core.cuh"
 
 namespace actk {
 
-constexpr int kCh = 64;      // channels per CTA
-constexpr int kT = 16;       // time steps per staged tile
-constexpr int kStages = 4;   // ring depth
-constexpr int kThreads = kCh + 32;
+constexpr int kCh = 64;  // channels per CTA == threads per CTA
+constexpr int kT = 16;   // time steps per tile
+template <typename T>
+constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : 4; }
 
 template <typename T>
 struct BranchDev {
@@ -30,156 +39,265 @@ struct BranchDev {
   const float *A, *Dskip, *dt_bias;
   T *ydir;
   int n_sel, n_tail;
+  int idx_iota;  // idx[p] == p for all p (n_sel == L): no index loads needed
 };
 template <typename T>
 struct MaskedParams {
   BranchDev<T> br[2];
   int first_branch;
   int Bp, L, D, xw;
+  int tma_ok;  // D % 64 == 0: box rows fill a whole smem row
+};
+struct alignas(64) BranchMaps {
+  CUtensorMap xz, xdbl, delta, ydir;
+};
+struct alignas(64) MaskedMaps {
+  BranchMaps m[2];
 };
 
 template <typename T>
-struct alignas(16) Stage {
+struct alignas(128) Stage {
   T u[kT][kCh];
   T dt[kT][kCh];
-  float bc[kT][2 * kN];                                  // fp32 B|C, what the compute warps read
-  T bc_raw[sizeof(T) == 4 ? 1 : kT][2 * kN];             // 16-bit landing zone (unused for fp32 I/O)
-  int row[kT];                                           // latent row to scatter to, -1 = tail token (dropped)
+  T bc[kT][2 * kN];
+};
+
+struct TileGeo {
+  int nrows;    // valid rows (16 except for the last tile)
+  int l_lo;     // lowest sequence position of the tile
+  int l_first;  // sequence position held by smem row 0 (can be negative for direction 1's last tile)
+  int row0;     // FAST only: latent row of smem row 0
+  bool fast;
 };
 
 template <typename T, bool POWER_A>
-__global__ void __launch_bounds__(kThreads) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P) {
-  __shared__ Stage<T> st[kStages];
-  __shared__ alignas(8) uint64_t full_bar[kStages], ready_bar[kStages], empty_bar[kStages];
+__global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P,
+                                                          const __grid_constant__ MaskedMaps M) {
+  constexpr int S = ring_stages<T>();
+  constexpr bool k16 = sizeof(T) == 2;
+  __shared__ Stage<T> st[S];
+  __shared__ alignas(128) T ybuf[2][kT][kCh];
+  __shared__ alignas(16) float bcf[k16 ? 2 : 1][k16 ? kT : 1][2 * kN];  // fp32 view of B|C for 16-bit I/O
+  __shared__ alignas(8) uint64_t full_bar[S];
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
   const int d0 = blockIdx.x * kCh;
   const int b = blockIdx.y;
   const int bi = P.first_branch + (blockIdx.z >> 1);
   const int k = blockIdx.z & 1;
-  const BranchDev<T> br = P.br[bi];   // by value: keeps the fields in registers instead of indexed constant loads
+  const BranchDev<T> br = P.br[bi];
+  const BranchMaps &maps = M.m[bi];
   const int n_sel = br.n_sel, n_tail = br.n_tail;
   const int Lp = n_sel + n_tail;
   const int D = P.D, L = P.L;
-  const int nch = min(kCh, D - d0);   // last channel block may be partial (D % 8 == 0 keeps rows 16-byte granular)
+  const int nch = min(kCh, D - d0);
   const int ntiles = (Lp + kT - 1) / kT;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 32);
-      mbar_init(&empty_bar[s], kCh / 32);
-    }
+    for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], kCh);
     mbar_fence_init();
+    if (P.tma_ok) {
+      tmap_prefetch(&maps.xz); tmap_prefetch(&maps.xdbl); tmap_prefetch(&maps.delta); tmap_prefetch(&maps.ydir);
+    }
   }
   __syncthreads();
 
-  if (warp == kCh / 32) {
-    // ------------------------------------------------------------------ producer warp
-    const uint32_t kRowBytes = nch * sizeof(T);
-    constexpr uint32_t kBcBytes = 2 * kN * sizeof(T);
-    const int r = lane & (kT - 1);
-    auto issue = [&](int tile) {
-      const int s = tile % kStages;
-      const uint32_t ph = (tile / kStages) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      const int p0 = tile * kT;
-      const int nrows = min(kT, Lp - p0);
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], nrows * (2 * kRowBytes + kBcBytes));
-      __syncwarp();
-      if (r < nrows) {
-        const int p = p0 + r;
-        const int l = k ? Lp - 1 - p : p;
-        if (lane < kT) {
-          const T *usrc, *bsrc;
-          int row = -1;
-          if (l < n_sel) {
-            row = __ldg(br.idx + l);
-            const size_t tok = (size_t)b * L + row;
-            usrc = br.xz + tok * D + d0;
-            bsrc = br.xdbl + tok * P.xw + k * 2 * kN;
-          } else {
-            const size_t tok = (size_t)b * n_tail + (l - n_sel);
-            usrc = br.tail + tok * D + d0;
-            bsrc = br.xdbl_tail + tok * P.xw + k * 2 * kN;
-          }
-          bulk_g2s(&st[s].u[r][0], usrc, kRowBytes, &full_bar[s]);
-          if (sizeof(T) == 4)
-            bulk_g2s(&st[s].bc[r][0], bsrc, kBcBytes, &full_bar[s]);
-          else
-            bulk_g2s(&st[s].bc_raw[r][0], bsrc, kBcBytes, &full_bar[s]);
-          st[s].row[r] = row;
-        } else {
-          const T *dsrc = br.delta + (((size_t)b * Lp + l) * 2 + k) * D + d0;
-          bulk_g2s(&st[s].dt[r][0], dsrc, kRowBytes, &full_bar[s]);
-        }
+  auto geo = [&](int t) {
+    TileGeo g;
+    const int p0 = t * kT;
+    g.nrows = min(kT, Lp - p0);
+    int l_hi;
+    if (k == 0) { g.l_lo = p0; l_hi = p0 + g.nrows - 1; g.l_first = p0; }
+    else { l_hi = Lp - 1 - p0; g.l_lo = l_hi - g.nrows + 1; g.l_first = l_hi - (kT - 1); }
+    g.fast = false; g.row0 = 0;
+    if (P.tma_ok && g.nrows == kT && l_hi < n_sel) {
+      if (br.idx_iota) { g.fast = true; g.row0 = g.l_lo; }
+      else {
+        const int r_lo = __ldg(br.idx + g.l_lo), r_hi = __ldg(br.idx + l_hi);
+        g.fast = (r_hi - r_lo) == kT - 1;
+        g.row0 = r_lo;
       }
-    };
-    const int pre = min(kStages - 1, ntiles);
-    for (int t = 0; t < pre; ++t) issue(t);
-    for (int t = 0; t < ntiles; ++t) {
-      // publish tile t first (it landed while the compute warps were busy with earlier tiles) ...
-      const int s = t % kStages;
-      const uint32_t ph = (t / kStages) & 1;
-      mbar_wait(&full_bar[s], ph);
-      if (sizeof(T) == 2) {
-        // 16 rows x 2 halves: each lane widens 16 values of one row to fp32
-        const int rr = lane >> 1, half = lane & 1;
-        const uint4 *src = reinterpret_cast<const uint4 *>(&st[s].bc_raw[rr][half * kN]);
-        float *dst = &st[s].bc[rr][half * kN];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          uint4 w = src[v];
-          const T *e = reinterpret_cast<const T *>(&w);
-          float4 lo = make_float4(IO<T>::ld(e + 0), IO<T>::ld(e + 1), IO<T>::ld(e + 2), IO<T>::ld(e + 3));
-          float4 hi = make_float4(IO<T>::ld(e + 4), IO<T>::ld(e + 5), IO<T>::ld(e + 6), IO<T>::ld(e + 7));
-          reinterpret_cast<float4 *>(dst)[2 * v] = lo;
-          reinterpret_cast<float4 *>(dst)[2 * v + 1] = hi;
-        }
-      }
-      mbar_arrive(&ready_bar[s]);
-      // ... then refill the stage the compute warps released last (blocks until they are done with tile t-1)
-      if (t + kStages - 1 < ntiles) issue(t + kStages - 1);
     }
-  } else {
-    // ------------------------------------------------------------------ compute warps: one channel per thread
-    const int c = tid;
-    const bool live = c < nch;
-    const int ch = k * D + d0 + (live ? c : 0);
-    ChannelScan<POWER_A> cs;
-    cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
-    T *ybase = br.ydir + ((size_t)k * P.Bp + b) * L * D + d0 + c;
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t % kStages;
-      const uint32_t ph = (t / kStages) & 1;
-      mbar_wait(&full_bar[s], ph);
-      mbar_wait(&ready_bar[s], ph);
-      const int nrows = live ? min(kT, Lp - t * kT) : 0;
-      if (nrows == kT) {
+    return g;
+  };
+
+  // source pointers of sequence position l (ragged path)
+  auto src_rows = [&](int l, const T *&usrc, const T *&bsrc) {
+    if (l < n_sel) {
+      const int row = br.idx_iota ? l : __ldg(br.idx + l);
+      const size_t tok = (size_t)b * L + row;
+      usrc = br.xz + tok * D + d0;
+      bsrc = br.xdbl + tok * P.xw + k * 2 * kN;
+    } else {
+      const size_t tok = (size_t)b * n_tail + (l - n_sel);
+      usrc = br.tail + tok * D + d0;
+      bsrc = br.xdbl_tail + tok * P.xw + k * 2 * kN;
+    }
+  };
+
+  auto issue_load = [&](int t, const TileGeo &g) {
+    Stage<T> &sg = st[t % S];
+    uint64_t *bar = &full_bar[t % S];
+    if (g.fast) {
+      if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)sizeof(Stage<T>));
+        tma_load_3d(&sg.dt[0][0], &maps.delta, k * D + d0, g.l_first, b, bar);
+        tma_load_3d(&sg.u[0][0], &maps.xz, d0, g.row0, b, bar);
+        tma_load_3d(&sg.bc[0][0], &maps.xdbl, k * 2 * kN, g.row0, b, bar);
+      }
+      mbar_arrive(bar);
+    } else {
+      constexpr int kPer = 16 / sizeof(T);                 // elements per 16-byte piece
+      const int cu = nch / kPer, cb = 2 * kN / kPer;       // pieces per u / delta row, per B|C row
+      const int per_row = 2 * cu + cb;
+      for (int id = tid; id < g.nrows * per_row; id += kCh) {
+        const int jj = id / per_row, w = id - jj * per_row;
+        const int l = g.l_lo + jj, j = l - g.l_first;
+        if (w < cu) {
+          const T *usrc, *bsrc;
+          src_rows(l, usrc, bsrc);
+          cp_async16(&sg.u[j][w * kPer], usrc + w * kPer);
+        } else if (w < 2 * cu) {
+          const T *dsrc = br.delta + (((size_t)b * Lp + l) * 2 + k) * D + d0;
+          cp_async16(&sg.dt[j][(w - cu) * kPer], dsrc + (w - cu) * kPer);
+        } else {
+          const T *usrc, *bsrc;
+          src_rows(l, usrc, bsrc);
+          cp_async16(&sg.bc[j][(w - 2 * cu) * kPer], bsrc + (w - 2 * cu) * kPer);
+        }
+      }
+      cp_async_arrive_noinc(bar);
+    }
+  };
+
+  T *ydst = br.ydir + ((size_t)k * P.Bp + b) * L * D + d0;
+  auto store_y = [&](int t, const TileGeo &g) {
+    if (g.fast) {
+      if (tid == 0) {
+        tma_store_3d(&maps.ydir, d0, g.row0, k * P.Bp + b, &ybuf[t & 1][0][0]);
+        bulk_commit();
+      }
+    } else {
+      constexpr int kPer = 16 / sizeof(T);
+      const int cu = nch / kPer;
+      for (int id = tid; id < g.nrows * cu; id += kCh) {
+        const int jj = id / cu, w = id - jj * cu;
+        const int l = g.l_lo + jj;
+        if (l < n_sel) {
+          const int row = br.idx_iota ? l : __ldg(br.idx + l);
+          const uint4 v = *reinterpret_cast<const uint4 *>(&ybuf[t & 1][l - g.l_first][w * kPer]);
+          *reinterpret_cast<uint4 *>(ydst + (size_t)row * D + w * kPer) = v;
+        }
+      }
+    }
+  };
+
+  const bool live = tid < nch;
+  const int ch = k * D + d0 + (live ? tid : 0);
+  ChannelScan<POWER_A> cs;
+  cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
+
+  for (int t = 0; t < min(S - 1, ntiles); ++t) issue_load(t, geo(t));
+
+  TileGeo prev = {};
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % S;
+    const TileGeo g = geo(t);
+    mbar_wait(&full_bar[s], (t / S) & 1);
+    if (k16) {  // widen this tile's B|C rows to fp32 once per CTA: thread -> (row tid/4, 8 values)
+      const int j = tid >> 2, q = (tid & 3) * 8;
+      uint4 w = *reinterpret_cast<const uint4 *>(&st[s].bc[j][q]);
+      const T *e = reinterpret_cast<const T *>(&w);
+      float4 lo = make_float4(IO<T>::ld(e + 0), IO<T>::ld(e + 1), IO<T>::ld(e + 2), IO<T>::ld(e + 3));
+      float4 hi = make_float4(IO<T>::ld(e + 4), IO<T>::ld(e + 5), IO<T>::ld(e + 6), IO<T>::ld(e + 7));
+      float4 *dst = reinterpret_cast<float4 *>(&bcf[t & 1][j][q]);
+      dst[0] = lo;
+      dst[1] = hi;
+    }
+    if (tid == 0) bulk_wait_read<0>();  // the y tile stored two iterations ago has left ybuf[t & 1]
+    __syncthreads();                    // B|C published; everyone is done with tile t-1 (its stage and y tile)
+    if (t > 0) store_y(t - 1, prev);
+    if (t + S - 1 < ntiles) issue_load(t + S - 1, geo(t + S - 1));
+
+    if (live) {
+      const T *us = &st[s].u[0][tid], *ds = &st[s].dt[0][tid];
+      const float *bcs = k16 ? &bcf[t & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
+      T *ys = &ybuf[t & 1][0][tid];
+      if (g.nrows == kT) {
+        if (k == 0) {
 #pragma unroll 4
-        for (int r = 0; r < kT; ++r) {
-          float y = cs.template step<true>(IO<T>::ld(&st[s].u[r][c]), IO<T>::ld(&st[s].dt[r][c]), st[s].bc[r]);
-          const int row = st[s].row[r];
-          if (row >= 0) IO<T>::st(ybase + (size_t)row * D, y);
+          for (int r = 0; r < kT; ++r) {
+            float y = cs.template step<true>(IO<T>::ld(us + r * kCh), IO<T>::ld(ds + r * kCh), bcs + r * 2 * kN);
+            IO<T>::st(ys + r * kCh, y);
+          }
+        } else {
+#pragma unroll 4
+          for (int r = 0; r < kT; ++r) {
+            const int j = kT - 1 - r;
+            float y = cs.template step<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh), bcs + j * 2 * kN);
+            IO<T>::st(ys + j * kCh, y);
+          }
         }
       } else {
-        for (int r = 0; r < nrows; ++r) {
-          float y = cs.template step<true>(IO<T>::ld(&st[s].u[r][c]), IO<T>::ld(&st[s].dt[r][c]), st[s].bc[r]);
-          const int row = st[s].row[r];
-          if (row >= 0) IO<T>::st(ybase + (size_t)row * D, y);
+        for (int r = 0; r < g.nrows; ++r) {
+          const int j = k ? kT - 1 - r : r;
+          float y = cs.template step<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh), bcs + j * 2 * kN);
+          IO<T>::st(ys + j * kCh, y);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
+    fence_proxy_async();  // make this thread's ybuf writes visible to the TMA store issued after the next barrier
+    prev = g;
   }
+  if (tid == 0) bulk_wait_read<0>();
+  __syncthreads();
+  if (ntiles > 0) store_y(ntiles - 1, prev);
+  if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// (inner, rows, outer) tensor with dense rows of `inner` elements; box = (box_inner, kT, 1)
+static int make_map(CUtensorMap *m, CUtensorMapDataType dt, int es, const void *base, uint64_t inner, uint64_t rows,
+                    uint64_t outer, uint32_t box_inner) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
+  cuuint64_t dims[3] = {inner, rows, outer};
+  cuuint64_t strides[2] = {inner * es, inner * rows * es};
+  cuuint32_t box[3] = {box_inner, (cuuint32_t)kT, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ACTK_OK;
 }
 
 template <typename T>
 static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   MaskedParams<T> P;
+  MaskedMaps M;
+  memset(&M, 0, sizeof(M));
   P.Bp = a->Bp; P.L = a->L; P.D = a->D; P.xw = a->xw;
+  P.tma_ok = (a->D % kCh == 0) ? 1 : 0;
+  const int es = sizeof(T);
+  const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                         : (a->dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   for (int i = 0; i < 2; ++i) {
     const actk_branch_args &s = a->br[i < a->n_branches ? i : 0];
     BranchDev<T> &d = P.br[i];
@@ -187,6 +305,15 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     d.xdbl_tail = (const T *)s.xdbl_tail; d.delta = (const T *)s.delta; d.idx = s.idx;
     d.A = s.A; d.Dskip = s.Dskip; d.dt_bias = s.dt_bias; d.ydir = (T *)s.ydir;
     d.n_sel = s.n_sel; d.n_tail = s.n_tail;
+    d.idx_iota = s.n_sel == a->L;   // ascending distinct rows in [0, L): all L of them means idx[p] == p
+    if (P.tma_ok && i < a->n_branches && s.n_sel > 0) {
+      const uint64_t Lp = (uint64_t)s.n_sel + s.n_tail;
+      int rc;
+      if ((rc = make_map(&M.m[i].xz, dt, es, s.xz, a->D, a->L, a->Bp, kCh))) return rc;
+      if ((rc = make_map(&M.m[i].xdbl, dt, es, s.xdbl, a->xw, a->L, a->Bp, 2 * kN))) return rc;
+      if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, Lp, a->Bp, kCh))) return rc;
+      if ((rc = make_map(&M.m[i].ydir, dt, es, s.ydir, a->D, a->L, 2ull * a->Bp, kCh))) return rc;
+    }
   }
   // group consecutive live branches that share an A kind into one launch (better tail balance)
   int i = 0;
@@ -197,9 +324,9 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     P.first_branch = i;
     dim3 grid((a->D + kCh - 1) / kCh, a->Bp, 2 * (j - i));
     if (a->br[i].a_kind == ACTK_A_POWER)
-      masked_scan_kernel<T, true><<<grid, kThreads, 0, stream>>>(P);
+      masked_scan_kernel<T, true><<<grid, kCh, 0, stream>>>(P, M);
     else
-      masked_scan_kernel<T, false><<<grid, kThreads, 0, stream>>>(P);
+      masked_scan_kernel<T, false><<<grid, kCh, 0, stream>>>(P, M);
     ACTK_CUDA_OK(cudaGetLastError());
     i = j;
   }
@@ -219,7 +346,7 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
   if (a->N != kN) ACTK_FAIL(ACTK_ERR_UNSUPPORTED, "masked_scan: d_state=%d, this build has %d", a->N, kN);
   if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->xw < 4 * kN)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d L=%d D=%d xw=%d", a->Bp, a->L, a->D, a->xw);
-  if (a->Bp > 65535) ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d exceeds grid.y", a->Bp);
+  if (a->Bp > 32767) ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d exceeds grid.y / 2", a->Bp);
   const int es = a->dtype == ACTK_F32 ? 4 : 2;
   if ((a->D * es) % 16 != 0)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: D=%d must be a multiple of %d (16-byte channel rows)", a->D, 16 / es);
