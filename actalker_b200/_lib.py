@@ -60,7 +60,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # ACTK_LIB_PATH selects a tuning variant built by actalker_b200.build.build(out=..., defs=...)
+    return os.environ.get("ACTK_LIB_PATH", _build.LIB_PATH)
 
 
 def load():

@@ -41,29 +41,34 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str = None, defs=()) -> str:
+    """Build the library.  `out`/`defs` produce a tuning variant (e.g. defs=["ACTK_POLY_PAIRS=3"]) beside the
+    default one; select it at run time with ACTK_LIB_PATH."""
+    variant = out is not None
+    out = out or LIB_PATH
+    if not variant and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     log = []
+    tag = os.path.splitext(os.path.basename(out))[0]
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, (tag + "_" if variant else "") + src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"]
+    cmd = [_nvcc(), "-shared", "-o", out, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
+    with open(os.path.join(LIB_DIR, "ptxas.log" if not variant else tag + "_ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

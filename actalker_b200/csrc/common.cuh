@@ -33,11 +33,26 @@ template <> struct IO<float> {
   static __device__ __forceinline__ float ld(const float *p) { return *p; }
   static __device__ __forceinline__ float rnd(float v) { return v; }
   static __device__ __forceinline__ void st(float *p, float v) { *p = v; }
+  // two adjacent elements (8-byte aligned)
+  static __device__ __forceinline__ void ld2(const float *p, float &a, float &b) {
+    float2 v = *reinterpret_cast<const float2 *>(p);
+    a = v.x; b = v.y;
+  }
+  static __device__ __forceinline__ void st2(float *p, float a, float b) {
+    *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+  }
 };
 template <> struct IO<__half> {
   static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
   static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
   static __device__ __forceinline__ void st(__half *p, float v) { *p = __float2half_rn(v); }
+  static __device__ __forceinline__ void ld2(const __half *p, float &a, float &b) {
+    float2 v = __half22float2(*reinterpret_cast<const __half2 *>(p));
+    a = v.x; b = v.y;
+  }
+  static __device__ __forceinline__ void st2(__half *p, float a, float b) {
+    *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(a, b);
+  }
 };
 template <> struct IO<__nv_bfloat16> {
   static __device__ __forceinline__ float ld(const __nv_bfloat16 *p) {
@@ -45,6 +60,13 @@ template <> struct IO<__nv_bfloat16> {
   }
   static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
   static __device__ __forceinline__ void st(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ void ld2(const __nv_bfloat16 *p, float &a, float &b) {
+    const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void st2(__nv_bfloat16 *p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b);
+  }
 };
 
 // ----------------------------------------------------------------------------- MUFU wrappers
@@ -93,6 +115,30 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// 2^t for two values t <= 0 on the FMA pipe instead of the MUFU unit (16 ex2/clk/SM is the wall of the
+// general-A scan): Cody-Waite split t = n + f with the 1.5*2^23 magic add, degree-5 polynomial for 2^f on
+// [-0.5, 0.5] constrained to p(0) = 1 (max rel. error 1.9e-7, the same class as ex2.approx), exponent inserted
+// with one integer shift-add.  8 packed FMA-pipe ops + 4 ALU ops per pair.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t t2) {
+  float tl, th;
+  upk(t2, tl, th);
+  const uint64_t t = pk(fmaxf(tl, -126.0f), fmaxf(th, -126.0f));
+  const uint64_t s = add2(t, pk(12582912.0f, 12582912.0f));           // low mantissa bits now hold round(t)
+  const uint64_t nf = add2(s, pk(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(nf, pk(-1.0f, -1.0f), t);
+  uint64_t p = pk(0.001326472731307149f, 0.001326472731307149f);
+  p = fma2(p, f, pk(0.009671512991189957f, 0.009671512991189957f));
+  p = fma2(p, f, pk(0.05550733581185341f, 0.05550733581185341f));
+  p = fma2(p, f, pk(0.24022242426872253f, 0.24022242426872253f));
+  p = fma2(p, f, pk(0.6931470036506653f, 0.6931470036506653f));
+  p = fma2(p, f, pk(1.0f, 1.0f));
+  float pl, ph, sl, sh;
+  upk(p, pl, ph);
+  upk(s, sl, sh);
+  return pk(__int_as_float(__float_as_int(pl) + (__float_as_int(sl) << 23)),
+            __int_as_float(__float_as_int(ph) + (__float_as_int(sh) << 23)));
 }
 
 // ----------------------------------------------------------------------------- mbarrier / TMA bulk copy

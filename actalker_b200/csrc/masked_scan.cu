@@ -29,6 +29,7 @@ namespace actk {
 
 constexpr int kCh = 64;  // channels per CTA == threads per CTA
 constexpr int kT = 16;   // time steps per tile
+constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::run)
 template <typename T>
 constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : 4; }
 
@@ -224,18 +225,29 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       const float *bcs = k16 ? &bcf[t & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
       T *ys = &ybuf[t & 1][0][tid];
       if (g.nrows == kT) {
+        // smem row of step r: r (direction 0) or 15 - r (direction 1); kGroup steps are software-pipelined
         if (k == 0) {
-#pragma unroll 4
-          for (int r = 0; r < kT; ++r) {
-            float y = cs.template step<true>(IO<T>::ld(us + r * kCh), IO<T>::ld(ds + r * kCh), bcs + r * 2 * kN);
-            IO<T>::st(ys + r * kCh, y);
+#pragma unroll 1
+          for (int r0 = 0; r0 < kT; r0 += kGroup) {
+            const T *u0 = us + r0 * kCh, *dl0 = ds + r0 * kCh;
+            const float *b0 = bcs + r0 * 2 * kN;
+            T *y0 = ys + r0 * kCh;
+            cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 + i * kCh); },
+                                          [&](int i) { return IO<T>::ld(dl0 + i * kCh); },
+                                          [&](int i) { return b0 + i * 2 * kN; },
+                                          [&](int i, float y) { IO<T>::st(y0 + i * kCh, y); });
           }
         } else {
-#pragma unroll 4
-          for (int r = 0; r < kT; ++r) {
-            const int j = kT - 1 - r;
-            float y = cs.template step<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh), bcs + j * 2 * kN);
-            IO<T>::st(ys + j * kCh, y);
+#pragma unroll 1
+          for (int r0 = 0; r0 < kT; r0 += kGroup) {
+            const int j0 = kT - 1 - r0;
+            const T *u0 = us + j0 * kCh, *dl0 = ds + j0 * kCh;
+            const float *b0 = bcs + j0 * 2 * kN;
+            T *y0 = ys + j0 * kCh;
+            cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 - i * kCh); },
+                                          [&](int i) { return IO<T>::ld(dl0 - i * kCh); },
+                                          [&](int i) { return b0 - i * 2 * kN; },
+                                          [&](int i, float y) { IO<T>::st(y0 - i * kCh, y); });
           }
         }
       } else {

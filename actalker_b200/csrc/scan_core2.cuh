@@ -1,0 +1,108 @@
+// Two-channels-per-thread form of the selective-scan recurrence (see scan_core.cuh for the math).
+//
+// Why two: with one channel per thread every step pulls the 32 B|C values of the step (128 B) into each lane's
+// registers with 8 broadcast LDS.128, i.e. 4 KB of shared-memory -> register traffic per warp-step.  Measured on
+// B200 (tools/microbench_step.cu) that LSU traffic costs about as much as the 24 packed FMA ops of the update
+// itself, and the mix saturates at ~117 SMSP-cycles per warp-step however many warps are resident.  Packing two
+// ADJACENT channels into each fp32x2 register (lane pair = same state n of channels 2c, 2c+1) lets one B_n / C_n
+// register feed both channels through the scalar-broadcast operand of FMUL2/FFMA2, halving the LDS traffic per
+// channel-step, and turns u / delta / y accesses into 32-bit bf16x2 words.
+#pragma once
+#include "common.cuh"
+
+namespace actk {
+
+struct StepIn2 {
+  uint64_t dt, x, u;  // (channel 0, channel 1)
+};
+
+template <bool POWER_A, int NPOLY = 0>   // NPOLY: states (highest n first) whose exp runs on the FMA pipe
+struct ChannelScan2 {
+  uint64_t h[kN];                  // h[n] = (h_c0[n], h_c1[n])
+  uint64_t a[POWER_A ? 1 : kN];    // A[c][n] * log2e pairs (POWER_A: only n = 0)
+  uint64_t dskip, bias;
+
+  __device__ __forceinline__ void init(const float *__restrict__ A0, const float *__restrict__ A1, float D0, float D1,
+                                       float b0, float b1) {
+    if (POWER_A) {
+      a[0] = pk(A0[0] * kLog2e, A1[0] * kLog2e);
+    } else {
+#pragma unroll
+      for (int n = 0; n < kN; ++n) a[n] = pk(A0[n] * kLog2e, A1[n] * kLog2e);
+    }
+#pragma unroll
+    for (int n = 0; n < kN; ++n) h[n] = pk(0.f, 0.f);
+    dskip = pk(D0, D1);
+    bias = pk(b0, b1);
+  }
+
+  template <bool SOFTPLUS>
+  __device__ __forceinline__ StepIn2 prologue(float u0, float u1, float d0, float d1) const {
+    StepIn2 s;
+    float t0, t1;
+    upk(add2(pk(d0, d1), bias), t0, t1);
+    if (SOFTPLUS) { t0 = softplus20(t0); t1 = softplus20(t1); }
+    s.dt = pk(t0, t1);
+    s.u = pk(u0, u1);
+    s.x = mul2(s.dt, s.u);
+    return s;
+  }
+
+  __device__ __forceinline__ void decay(uint64_t dt, uint64_t (&p)[kN]) const {
+    if (POWER_A) {
+      // r = exp(dt*A_0) per channel; p[n] = r^(n+1) by a depth-3 multiply tree, r^8 straight from the MUFU
+      float t0, t1;
+      upk(mul2(dt, a[0]), t0, t1);
+      p[0] = pk(ex2(t0), ex2(t1));
+      p[7] = pk(ex2(8.0f * t0), ex2(8.0f * t1));
+      p[1] = mul2(p[0], p[0]);
+      p[2] = mul2(p[1], p[0]);
+      p[3] = mul2(p[1], p[1]);
+      p[4] = mul2(p[3], p[0]);
+      p[5] = mul2(p[3], p[1]);
+      p[6] = mul2(p[3], p[2]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) p[8 + n] = mul2(p[7], p[n]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < kN; ++n) {
+        const uint64_t t2 = mul2(dt, a[n]);
+        if (n >= kN - NPOLY) {
+          p[n] = ex2_poly2(t2);
+        } else {
+          float lo, hi;
+          upk(t2, lo, hi);
+          p[n] = pk(ex2(lo), ex2(hi));
+        }
+      }
+    }
+  }
+
+  // h update + output for both channels.  bc: 32 fp32 in shared memory (B[0..15], C[0..15]).
+  __device__ __forceinline__ uint64_t apply(const uint64_t (&p)[kN], const StepIn2 &s, const float *__restrict__ bc) {
+    const float4 *bc4 = reinterpret_cast<const float4 *>(bc);
+    uint64_t y[4] = {pk(0.f, 0.f), pk(0.f, 0.f), pk(0.f, 0.f), pk(0.f, 0.f)};
+#pragma unroll
+    for (int q = 0; q < kN / 4; ++q) {
+      const float4 B = bc4[q], C = bc4[kN / 4 + q];
+      const float Bv[4] = {B.x, B.y, B.z, B.w}, Cv[4] = {C.x, C.y, C.z, C.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = 4 * q + i;
+        h[n] = fma2(p[n], h[n], mul2(s.x, pk(Bv[i], Bv[i])));
+        y[i] = fma2(pk(Cv[i], Cv[i]), h[n], y[i]);
+      }
+    }
+    return fma2(dskip, s.u, add2(add2(y[0], y[1]), add2(y[2], y[3])));
+  }
+
+  template <bool SOFTPLUS>
+  __device__ __forceinline__ uint64_t step(float u0, float u1, float d0, float d1, const float *__restrict__ bc) {
+    StepIn2 s = prologue<SOFTPLUS>(u0, u1, d0, d1);
+    uint64_t p[kN];
+    decay(s.dt, p);
+    return apply(p, s, bc);
+  }
+};
+
+}  // namespace actk

@@ -1,0 +1,80 @@
+// Microbenchmark of the raw instruction rates the scan depends on (B200, sm_100a): scalar FFMA, packed FFMA2,
+// FMUL2 with a broadcast operand, MUFU.EX2, and broadcast LDS.128 — each as 16 independent chains per thread so
+// that only pipe throughput (not latency) is measured.  Prints SMSP-cycles per warp-instruction.
+#include <cstdio>
+
+#include "../actalker_b200/csrc/common.cuh"
+namespace actk {
+void set_error(const char *, ...) {}
+}
+using namespace actk;
+
+template <int OP>
+__global__ void __launch_bounds__(128) rate_kernel(float *out, const float *in, int iters) {
+  __shared__ alignas(16) float sm[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = in[i];
+  __syncthreads();
+  float f[16];
+  uint64_t v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { f[i] = in[i] + threadIdx.x; v[i] = pk(f[i], f[i] + 1.f); }
+  const float a = in[17], b = in[18];
+  const uint64_t a2 = pk(a, a), b2 = pk(b, b + 1e-3f);
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (OP == 0) f[i] = fmaf(f[i], a, b);
+      if (OP == 1) v[i] = fma2(v[i], a2, b2);
+      if (OP == 2) v[i] = mul2(v[i], a2);
+      if (OP == 3) f[i] = ex2(f[i]);
+      if (OP == 4) {
+        float4 x = *reinterpret_cast<const float4 *>(&sm[((it * 16 + i) * 4) & 1020]);
+        acc += x.x + x.w;   // 2 FADD per LDS.128 (needed to keep the load alive)
+      }
+      if (OP == 5) {  // the apply() pattern: FMUL2 (bcast) + FFMA2 + FFMA2 per state pair, operands from registers
+        uint64_t d = mul2(a2, v[(i + 1) & 15]);
+        v[i] = fma2(b2, v[i], d);
+        v[(i + 8) & 15] = fma2(a2, v[i], v[(i + 8) & 15]);
+      }
+    }
+  }
+  float r = acc;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { float lo, hi; upk(v[i], lo, hi); r += f[i] + lo + hi; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int OP>
+static void run(const char *name, int inst_per_iter, float *out, const float *in) {
+  const int iters = 2048;
+  for (int warps_per_sm : {4, 16, 32}) {
+    int ctas = 148 * warps_per_sm / 4;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    rate_kernel<OP><<<ctas, 128>>>(out, in, iters);
+    cudaEventRecord(a);
+    rate_kernel<OP><<<ctas, 128>>>(out, in, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    double winst = (double)ctas * 4 * iters * inst_per_iter;
+    printf("%-34s warps/SM %2d: %.2f SMSP-cycles per warp-instruction\n", name, warps_per_sm,
+           ms * 1e-3 * 1.965e9 / (winst / (148 * 4)));
+  }
+}
+
+int main() {
+  float *in, *out;
+  cudaMalloc(&in, 4096);
+  cudaMalloc(&out, 148 * 8 * 128 * 4 * 4);
+  cudaMemset(in, 0, 4096);
+  run<0>("FFMA (scalar)", 16, out, in);
+  run<1>("FFMA2 (packed)", 16, out, in);
+  run<2>("FMUL2 (packed)", 16, out, in);
+  run<3>("MUFU.EX2", 16, out, in);
+  run<4>("LDS.128 broadcast (+2 FADD)", 16, out, in);
+  run<5>("FMUL2+FFMA2+FFMA2 triple", 48, out, in);
+  return cudaDeviceSynchronize() != cudaSuccess;
+}
