@@ -305,7 +305,9 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   MaskedMaps M;
   memset(&M, 0, sizeof(M));
   P.Bp = a->Bp; P.L = a->L; P.D = a->D; P.xw = a->xw;
-  P.tma_ok = (a->D % kCh == 0) ? 1 : 0;
+  // boxes are always 64 channels wide; a last partial channel block relies on TMA's out-of-bounds handling
+  // (zero fill on load, clipping on store), so any D >= 64 qualifies (channel-sharded slices such as D/8 = 80)
+  P.tma_ok = (a->D >= kCh) ? 1 : 0;
   const int es = sizeof(T);
   const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                          : (a->dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16

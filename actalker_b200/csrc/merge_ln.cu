@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ M
       for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
     }
   }
+  if (!a.layernorm) {   // channel-sharded path: emit the merged sums, LayerNorm follows the all-gather
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) store8((T *)a.out + off + 8 * (lane + 32 * i), x[i]);
+    return;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / D;
@@ -103,6 +109,69 @@ __global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ M
       store8((T *)a.out + off + 8 * v, o);
     }
   }
+}
+
+// LayerNorm over channel slices gathered from P ranks: in (P, rows, Ds) -> out (rows, P*Ds).
+// One warp per row; slice p of a row sits at in + (p*rows + row)*Ds (the layout NCCL all-gather produces).
+template <typename T, int VPL>
+__global__ void __launch_bounds__(128) gathered_ln_kernel(const T *__restrict__ in, const T *__restrict__ gamma,
+                                                          const T *__restrict__ beta, T *__restrict__ out, int parts,
+                                                          long long rows, int Ds, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int D = parts * Ds, nvec = D >> 3;
+  float x[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      const int ch = 8 * v, p = ch / Ds;
+      load8(in + ((size_t)p * rows + row) * Ds + (ch - p * Ds), x[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += x[i][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * i < nvec)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { float d = x[i][e] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / D + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float g[8], bt[8], o[8];
+      load8(gamma + 8 * v, g);
+      load8(beta + 8 * v, bt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf((x[i][e] - mean) * rstd, g[e], bt[e]);
+      store8(out + (size_t)row * D + 8 * v, o);
+    }
+  }
+}
+
+template <typename T>
+static int launch_gathered(const void *in, const void *gamma, const void *beta, void *out, int parts, long long rows,
+                           int Ds, float eps, cudaStream_t stream) {
+  const int vpl = ((parts * Ds >> 3) + 31) / 32;
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+#define ACTK_GLN(V) gathered_ln_kernel<T, V><<<grid, 128, 0, stream>>>((const T *)in, (const T *)gamma, (const T *)beta, (T *)out, parts, rows, Ds, eps)
+  if (vpl <= 4) ACTK_GLN(4);
+  else if (vpl <= 8) ACTK_GLN(8);
+  else if (vpl <= 16) ACTK_GLN(16);
+  else ACTK_GLN(32);
+#undef ACTK_GLN
+  ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
 }
 
 template <typename T>
@@ -130,7 +199,8 @@ extern "C" int actk_merge_layernorm_fwd(const actk_merge_ln_args *a, void *strea
   if (a->n_branches < 1 || a->n_branches > 2) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: n_branches=%d", a->n_branches);
   if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->D % 8 != 0 || a->D > 8192)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "merge_ln: Bp=%d L=%d D=%d (D must be a multiple of 8, <= 8192)", a->Bp, a->L, a->D);
-  if (!a->gamma || !a->beta || !a->out) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: gamma, beta and out are required");
+  if (!a->out || (a->layernorm && (!a->gamma || !a->beta)))
+    ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: out (and gamma, beta when layernorm != 0) are required");
   for (int i = 0; i < a->n_branches; ++i) {
     if (!a->xz[i] || !a->ydir[i] || !a->selected[i]) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: branch %d has a NULL pointer", i);
     if ((reinterpret_cast<uintptr_t>(a->xz[i]) | reinterpret_cast<uintptr_t>(a->ydir[i])) & 15)
@@ -143,5 +213,22 @@ extern "C" int actk_merge_layernorm_fwd(const actk_merge_ln_args *a, void *strea
     case ACTK_F32: return launch_merge<float>(a, st);
     case ACTK_F16: return launch_merge<__half>(a, st);
     default: return launch_merge<__nv_bfloat16>(a, st);
+  }
+}
+
+extern "C" int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int Ds, const void *gamma,
+                                           const void *beta, float eps, void *out, int dtype, void *stream) {
+  if (dtype < ACTK_F32 || dtype > ACTK_BF16) ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "gathered_ln: dtype=%d", dtype);
+  if (!in || !gamma || !beta || !out) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gathered_ln: NULL pointer");
+  if (parts <= 0 || rows <= 0 || Ds <= 0 || Ds % 8 != 0 || (long long)parts * Ds > 8192)
+    ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "gathered_ln: parts=%d rows=%lld Ds=%d (Ds %% 8 == 0, parts*Ds <= 8192)", parts, rows, Ds);
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+       reinterpret_cast<uintptr_t>(beta)) & 15)
+    ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "gathered_ln: pointer not aligned to 16 bytes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case ACTK_F32: return launch_gathered<float>(in, gamma, beta, out, parts, rows, Ds, eps, st);
+    case ACTK_F16: return launch_gathered<__half>(in, gamma, beta, out, parts, rows, Ds, eps, st);
+    default: return launch_gathered<__nv_bfloat16>(in, gamma, beta, out, parts, rows, Ds, eps, st);
   }
 }

@@ -159,17 +159,20 @@ class SS2D_Unit(nn.Module):
         if not xt.is_contiguous():
             xt = xt.contiguous()
         idx = torch.arange(L, dtype=torch.int32, device=x.device)
-        ydir = _scan_branches([self], [xt], [None], [idx], [L], Bsz, L)[0]      # (2, B, L, D)
+        ydir = _scan_branches([self], [xt], [None], [idx], [L], Bsz, L)[0][0]   # (2, B, L, D)
         return (ydir[0] + ydir[1]).permute(0, 2, 1)
 
     def forward(self, input):
         return self.forward_core(input)
 
 
-def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None):
+def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None, ch_slice=None):
     """Shared launcher: x_proj / dt_proj GEMMs (cuBLAS) + one actk_masked_scan_fwd for all given branches.
     xzs[i]: (Bp, L, D) contiguous; tails[i]: (Bp, n_tail, D) or None; idxs[i]: int32 (n_sel,).
-    Returns per-branch ydir tensors (2, Bp, L, D); rows of unselected tokens are uninitialised."""
+    ch_slice=(lo, hi): scan only channels [lo, hi) of every direction (multi-GPU channel sharding): x_proj still
+    contracts over all D channels (B|C are replicated), delta / A / D / dt_bias / u are sliced.
+    Returns per-branch (ydir (2, Bp, L, Dk), xz_k (Bp, L, Dk)) with Dk = hi - lo (D when unsliced); rows of
+    unselected tokens of ydir are uninitialised."""
     lib = _lib.load()
     x0 = xzs[0]
     if not x0.is_cuda:
@@ -177,16 +180,20 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
     if x0.dtype not in _DTYPES:
         raise RuntimeError(f"unsupported activation dtype {x0.dtype}")
     D = x0.shape[-1]
+    lo, hi = (0, D) if ch_slice is None else ch_slice
+    Dk = hi - lo
+    sliced = Dk != D
     args = _lib.MaskedScanArgs()
-    args.n_branches, args.Bp, args.L, args.D, args.N = len(units), Bp, L, D, _N
+    args.n_branches, args.Bp, args.L, args.D, args.N = len(units), Bp, L, Dk, _N
     args.dtype = _DTYPES[x0.dtype]
     keep, outs = [], []
     for i, unit in enumerate(units):
         dv = unit.derived()
         xz, tail, n_sel = xzs[i], tails[i], n_sels[i]
         n_tail = 0 if tail is None else tail.shape[1]
-        ydir = torch.empty((2, Bp, L, D), dtype=xz.dtype, device=xz.device)
-        outs.append(ydir)
+        ydir = torch.empty((2, Bp, L, Dk), dtype=xz.dtype, device=xz.device)
+        xz_k = xz[..., lo:hi].contiguous() if sliced else xz
+        outs.append((ydir, xz_k))
         b = args.br[i]
         b.n_sel, b.n_tail, b.a_kind = n_sel, n_tail, dv["a_kind"]
         if n_sel == 0:
@@ -201,13 +208,18 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         if n_tail:
             xdbl_tail = F.linear(tail, w_x)                                # (Bp, n_tail, xw)
             dtr = torch.cat([dtr, xdbl_tail[..., 4 * _N:]], dim=1)
-        delta = torch.matmul(dtr, dv["w_dt"].to(xz.dtype))                 # (Bp, Lp, 2D), sequence order
+        w_dt, A, Dsk, dtb = dv["w_dt"].to(xz.dtype), dv["A"], dv["Ds"], dv["dt_bias"]
+        if sliced:   # columns / rows [k*D + lo, k*D + hi) of both directions
+            cols = torch.cat([torch.arange(k * D + lo, k * D + hi, device=xz.device) for k in range(2)])
+            w_dt, A, Dsk, dtb = w_dt[:, cols].contiguous(), A[cols].contiguous(), Dsk[cols].contiguous(), dtb[cols].contiguous()
+            tail = None if tail is None else tail[..., lo:hi].contiguous()
+        delta = torch.matmul(dtr, w_dt)                                    # (Bp, Lp, 2*Dk), sequence order
         if args.xw not in (0, xw):
             raise RuntimeError("branches disagree on the x_proj width")
         args.xw = xw
-        b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
-        b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(dv["A"]), _ptr(dv["Ds"]), _ptr(dv["dt_bias"]), _ptr(ydir)
-        keep += [xdbl, xdbl_tail, delta, w_x]
+        b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz_k), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
+        b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(A), _ptr(Dsk), _ptr(dtb), _ptr(ydir)
+        keep += [xdbl, xdbl_tail, delta, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
     if any(n > 0 for n in n_sels):
         with torch.cuda.device(x0.device), _timed("masked_scan", x0.device):
             _lib.check(lib.actk_masked_scan_fwd(ct.byref(args), _stream(x0)), "actk_masked_scan_fwd")
@@ -249,30 +261,34 @@ class SS2D_cond_v10(nn.Module):
             raise NotImplementedError("only scan_type='sweep' is live in the reference")
         self.mask_cache = MaskIndexCache()
 
-    def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex):
-        """Both branches' gather -> bidirectional scan -> scatter, then merge + out_norm.  -> (Bp, L, D)."""
+    def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None):
+        """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
+        ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
+        ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
+        LayerNorm needs every channel and runs after the all-gather (sharded.py)."""
         lib = _lib.load()
         Bp, L, D = xz1.shape
-        ydirs = _scan_branches([self.audio_unit, self.exp_unit], [xz1, xz2], [tail1, tail2], [m1.idx, m2.idx],
-                               [m1.n_sel, m2.n_sel], Bp, L, idx64s=[m1.idx64, m2.idx64])
-        out = torch.empty_like(xz1)
+        res = _scan_branches([self.audio_unit, self.exp_unit], [xz1, xz2], [tail1, tail2], [m1.idx, m2.idx],
+                             [m1.n_sel, m2.n_sel], Bp, L, idx64s=[m1.idx64, m2.idx64], ch_slice=ch_slice)
+        Dk = res[0][1].shape[-1]
+        out = torch.empty((Bp, L, Dk), dtype=xz1.dtype, device=xz1.device)
         a = _lib.MergeLnArgs()
-        for i, (xz, yd, m) in enumerate(((xz1, ydirs[0], m1), (xz2, ydirs[1], m2))):
-            a.xz[i], a.ydir[i], a.selected[i] = xz.data_ptr(), yd.data_ptr(), m.selected.data_ptr()
-        gamma, beta = self.out_norm.weight.to(xz1.dtype), self.out_norm.bias.to(xz1.dtype)
-        a.gamma, a.beta, a.out = _ptr(gamma), _ptr(beta), _ptr(out)
-        a.eps, a.n_branches, a.Bp, a.L, a.D, a.dtype = self.out_norm.eps, 2, Bp, L, D, _DTYPES[xz1.dtype]
+        for i, ((yd, xz_k), m) in enumerate(zip(res, (m1, m2))):
+            a.xz[i], a.ydir[i], a.selected[i] = xz_k.data_ptr(), yd.data_ptr(), m.selected.data_ptr()
+        a.out = _ptr(out)
+        a.layernorm = 1 if ch_slice is None else 0
+        if a.layernorm:
+            gamma, beta = self.out_norm.weight.to(xz1.dtype), self.out_norm.bias.to(xz1.dtype)
+            a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+        a.eps, a.n_branches, a.Bp, a.L, a.D, a.dtype = self.out_norm.eps, 2, Bp, L, Dk, _DTYPES[xz1.dtype]
         with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
         return out
 
-    def forward(self, x, id_emb, conds, masks):
-        # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
-        # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("actalker_b200.SS2D_cond_v10 is forward-only (the reference's inference path, "
-                                      "pipeline ...two_ip.py:351); call it under torch.no_grad()")
-        Bp, L, _ = x.shape
+    def project_inputs(self, x, id_emb, conds, masks):
+        """The dense front half of forward (mamba_layer.py:1958-1961, 1966, 1972, 1977): in_proj of both
+        branches, id / condition projections, cached mask indices."""
+        L = x.shape[1]
         audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
         id_tok = self.act2(self.id_proj(id_emb))
         xz1 = self.in_proj1(x)
@@ -281,5 +297,13 @@ class SS2D_cond_v10(nn.Module):
         m2 = self.mask_cache.get(masks[1], L)
         tail1 = torch.cat([id_tok, self.act1(self.audio_proj(audio_cond))], dim=1)
         tail2 = torch.cat([id_tok, self.act2(self.exp_proj(exp_cond))], dim=1)
-        y = self.scan_core(xz1.contiguous(), xz2.contiguous(), tail1.contiguous(), tail2.contiguous(), m1, m2)
+        return xz1.contiguous(), xz2.contiguous(), tail1.contiguous(), tail2.contiguous(), m1, m2
+
+    def forward(self, x, id_emb, conds, masks):
+        # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
+        # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("actalker_b200.SS2D_cond_v10 is forward-only (the reference's inference path, "
+                                      "pipeline ...two_ip.py:351); call it under torch.no_grad()")
+        y = self.scan_core(*self.project_inputs(x, id_emb, conds, masks))
         return self.out_proj(y)

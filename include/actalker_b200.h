@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 1
+#define ACTK_ABI_VERSION 2
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -144,9 +144,17 @@ typedef struct {
   int n_branches;
   int Bp, L, D;
   int dtype;
+  int layernorm; /* 1: as above.  0: out[r] = round(t_1 + t_0) only (gamma/beta unused) — the channel-sharded
+                    multi-GPU path, where LayerNorm can only run after the all-gather of the channel slices */
 } actk_merge_ln_args;
 
 int actk_merge_layernorm_fwd(const actk_merge_ln_args *args, void *stream);
+
+/* (3b) LayerNorm over channel slices gathered from `parts` ranks (the layout an NCCL all-gather of per-rank
+ *      (rows, Ds) buffers produces): in (parts, rows, Ds) -> out (rows, parts*Ds), statistics in fp32 over all
+ *      parts*Ds channels (mamba_layer.py:1984 needs complete channels).  Ds % 8 == 0, parts*Ds <= 8192. */
+int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int Ds, const void *gamma, const void *beta,
+                                float eps, void *out, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) A-structure probe.  Writes *flag_dev = ACTK_A_POWER if |A[d][n] - (n+1)*A[d][0]| <=

@@ -1,0 +1,116 @@
+"""Multi-GPU path: the partition plan and the all-gather plumbing on CPU with world_size-2 gloo, and the
+channel-sliced compute on one GPU with the ranks emulated one after another (B200_PROFILING.md: never co-run
+waiting kernels of several ranks on one GPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from actalker_b200.sharded import ShardPlan, all_gather_slices
+
+
+def test_shard_plan_bounds():
+    p = ShardPlan("channel", 8, 640, 8)
+    assert p.all_bounds() == [(80 * r, 80 * r + 80) for r in range(8)]
+    assert ShardPlan("channel", 2, 2560, 8).bounds(1) == (1280, 2560)
+    with pytest.raises(ValueError):
+        ShardPlan("channel", 3, 640, 8)            # 640 / 3 is not 16-byte granular
+    b = ShardPlan("batch", 8, 25)                   # 25 frames over 8 GPUs: 4 3 3 3 3 3 3 3
+    sizes = [hi - lo for lo, hi in b.all_bounds()]
+    assert sizes == [4, 3, 3, 3, 3, 3, 3, 3] and b.bounds(0)[0] == 0 and b.bounds(7)[1] == 25
+    assert all(b.bounds(r)[1] == b.bounds(r + 1)[0] for r in range(7))
+    assert ShardPlan("batch", 4, 100).all_bounds() == [(25 * r, 25 * r + 25) for r in range(4)]
+    with pytest.raises(ValueError):
+        ShardPlan("rows", 2, 8)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                                   # same full tensor on every rank
+        Bp, L, D = 3, 10, 32
+        full = torch.randn(Bp, L, D)
+        plan = ShardPlan("channel", world, D, 8)
+        lo, hi = plan.bounds(rank)
+        gathered = all_gather_slices(full[..., lo:hi].contiguous())        # (P, Bp, L, Ds)
+        assert gathered.shape == (world, Bp, L, (hi - lo))
+        for p in range(world):
+            plo, phi = plan.bounds(p)
+            assert torch.equal(gathered[p], full[..., plo:phi])
+        # the gathered layout, read slice-major, is the full tensor: what actk_gathered_layernorm_fwd normalises
+        rebuilt = gathered.permute(1, 2, 0, 3).reshape(Bp, L, D)
+        assert torch.equal(rebuilt, full)
+        want = torch.nn.functional.layer_norm(full, (D,))
+        assert torch.allclose(torch.nn.functional.layer_norm(rebuilt, (D,)), want)
+        # batch mode: ranks own disjoint frame ranges that tile B'
+        bp = ShardPlan("batch", world, 7)
+        mine = torch.zeros(7)
+        mine[slice(*bp.bounds(rank))] = 1
+        dist.all_reduce(mine)
+        assert torch.equal(mine, torch.ones(7))
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_plumbing_with_gloo_world_size_2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d_model,world", [(64, 2), (320, 8), (96, 4)])
+def test_channel_sharded_layer_equals_unsharded(dtype, d_model, world):
+    """Ranks emulated sequentially on one GPU: every rank's slice scan + merge, stacked the way the all-gather
+    would deliver them, normalised by the gathered-LayerNorm kernel, must reproduce the unsharded layer."""
+    from actalker_b200 import SS2D_cond_v10
+    from actalker_b200.sharded import ShardedSS2DCondV10
+    torch.manual_seed(7)
+    side = 10
+    layer = SS2D_cond_v10(d_model=d_model, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=side,
+                          scan_type="sweep", num_direction=2).eval()
+    with torch.no_grad():
+        for u in (layer.audio_unit, layer.exp_unit):
+            u.A_logs.add_(0.3 * torch.randn_like(u.A_logs))
+    if dtype != torch.float32:
+        layer = layer.to(dtype)
+        for n, p in layer.named_parameters():
+            if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias")):
+                p.data = p.data.float()
+    layer = layer.cuda()
+    Bp, L = 3, side * side
+    x = torch.randn(Bp, L, d_model, device="cuda").to(dtype)
+    idm = torch.randn(Bp, 1, 64, device="cuda").to(dtype)
+    cd = torch.randn(Bp, 33, 64, device="cuda").to(dtype)
+    rect = torch.zeros(1, 1, 80, 80, device="cuda", dtype=dtype)
+    rect[:, :, 16:64, 8:72] = 1
+    masks = [torch.ones(1, 1, 80, 80, device="cuda", dtype=dtype), rect]
+    wrap = ShardedSS2DCondV10(layer, mode="channel")
+    plan = ShardPlan("channel", world, layer.d_inner, 8)
+    with torch.no_grad():
+        want = layer(x, idm, cd, masks)
+        proj = layer.project_inputs(x, idm, cd, masks)
+        parts = [layer.scan_core(*proj, ch_slice=plan.bounds(r)) for r in range(world)]
+        gathered = torch.stack(parts, dim=0)
+        got = layer.out_proj(wrap.gathered_layernorm(gathered))
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(got.float(), want.float(), rtol=tol, atol=tol), (got.float() - want.float()).abs().max()
