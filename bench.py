@@ -209,18 +209,23 @@ def run_ours(args, rank, world, local_rank):
         kern = {}
         for name, s, e in events:
             kern.setdefault(name, []).append(s.elapsed_time(e))
-        # ---------------- end-to-end through the public module call with host buffers
-        for _ in range(2):
-            y = layer(hx.to(dev, non_blocking=True), hid.to(dev, non_blocking=True), hcd.to(dev, non_blocking=True), masks)
-            hy.copy_(y, non_blocking=True)
+        # ---------------- end-to-end through the public host-buffer API: every step uploads its inputs from pinned
+        # host memory and downloads its result; HostStreamedLayer overlaps step i+1's H2D and step i-1's D2H with
+        # step i's compute (three streams, double-buffered staging) — all bytes still move inside the timed region
+        from actalker_b200.host_api import HostStreamedLayer
+        runner = HostStreamedLayer(layer)
+        hys = [hy, torch.empty_like(hy).pin_memory()]
+        for i in range(3):
+            runner.submit(hx, hid, hcd, masks, hys[i % 2])
+        runner.drain()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
-        s2.record()
-        for _ in range(args.steps):
-            y = layer(hx.to(dev, non_blocking=True), hid.to(dev, non_blocking=True), hcd.to(dev, non_blocking=True), masks)
-            hy.copy_(y, non_blocking=True)
-        e2.record()
+        s2.record(runner.h2d)
+        for i in range(args.steps):
+            runner.submit(hx, hid, hcd, masks, hys[i % 2])
+        e2.record(runner.d2h)
+        runner.drain()
         barrier()
         wall_e2e = (time.perf_counter() - t0) * 1e3
         ms_e2e_total = max(s2.elapsed_time(e2), 0.0)
@@ -267,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": tokens / (ms_e2e * 1e-3) / 1e9, "unit": "Gtokens/s",
                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (hx, hid, hcd)),
                 "d2h_bytes_per_step": hy.numel() * hy.element_size(), "ms_per_step": ms_e2e,
+                "api": "actalker_b200.host_api.HostStreamedLayer.submit (H2D | compute | D2H streams, depth 2)",
                 "host_wall_ms_per_step": wall_e2e / args.steps},
         "gpu_launches": (3 if channel else 2) * args.steps,
         "clocks": sampler.summary(),

@@ -256,3 +256,24 @@ def test_layer_is_forward_only_and_says_so():
     with pytest.raises(NotImplementedError):
         layer(torch.randn(1, 64, 32, device="cuda"), torch.randn(1, 1, 64, device="cuda"),
               torch.randn(1, 33, 64, device="cuda"), [ones, ones])
+
+
+def test_host_streamed_layer_matches_direct_calls():
+    """The host-buffer API (three streams, double-buffered staging) returns what direct device calls return,
+    for every submission, including when consecutive submissions reuse a staging slot."""
+    from actalker_b200 import SS2D_cond_v10
+    from actalker_b200.host_api import HostStreamedLayer
+    torch.manual_seed(11)
+    layer = SS2D_cond_v10(d_model=64, d_cond=128, cond_size=32, dropout=0.1, d_state=16, size=12,
+                          scan_type="sweep", num_direction=2).eval().cuda()
+    ones = torch.ones(1, 1, 96, 96, device="cuda")
+    work = [(torch.randn(3, 144, 64).pin_memory(), torch.randn(3, 1, 128).pin_memory(),
+             torch.randn(3, 33, 128).pin_memory(), torch.empty(3, 144, 64).pin_memory()) for _ in range(5)]
+    runner = HostStreamedLayer(layer)
+    for x, idm, cd, out in work:
+        runner.submit(x, idm, cd, [ones, ones], out)
+    runner.drain()
+    with torch.no_grad():
+        for x, idm, cd, out in work:
+            want = layer(x.cuda(), idm.cuda(), cd.cuda(), [ones, ones]).cpu()
+            assert torch.equal(out, want)

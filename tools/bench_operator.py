@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Time the operator-contract kernel (selective_scan_fn, channels-first) at the shapes the reference issues for
+BASELINE config 2 (mamba_layer.py:1532-1538): u, delta (25, 1280, L'), B, C (25, 2, 16, L'), bf16."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from actalker_b200 import selective_scan_fn, _lib
+
+def main():
+    dev = "cuda"
+    for dtype in (torch.bfloat16, torch.float32):
+        for Lp in (5217, 5186):
+            g = torch.Generator(device=dev).manual_seed(0)
+            B, Dm = 25, 1280
+            u = torch.randn(B, Dm, Lp, device=dev, generator=g).to(dtype)
+            delta = torch.randn(B, Dm, Lp, device=dev, generator=g).to(dtype)
+            A = -torch.exp(torch.randn(Dm, 16, device=dev, generator=g))
+            Bm = torch.randn(B, 2, 16, Lp, device=dev, generator=g).to(dtype)
+            Cm = torch.randn(B, 2, 16, Lp, device=dev, generator=g).to(dtype)
+            Dv = torch.ones(Dm, device=dev); bias = torch.randn(Dm, device=dev) - 2
+            for _ in range(3):
+                selective_scan_fn(u, delta, A, Bm, Cm, Dv, None, bias, True)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); s.record()
+            n = 10
+            for _ in range(n):
+                selective_scan_fn(u, delta, A, Bm, Cm, Dv, None, bias, True)
+            e.record(); torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / n
+            q = _lib.load().actk_scan_algorithmic_bytes(B, Lp, Dm, 2, 16, u.element_size())
+            print(f"selective_scan_fn {str(dtype)[6:]:8s} L'={Lp}: {ms:.3f} ms  {q / ms / 1e6:.0f} GB/s algorithmic")
+
+if __name__ == "__main__":
+    main()
