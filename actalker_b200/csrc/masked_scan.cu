@@ -47,7 +47,12 @@ struct MaskedParams {
   BranchDev<T> br[2];
   int first_branch;
   int Bp, L, D, xw;
-  int tma_ok;  // D % 64 == 0: box rows fill a whole smem row
+  int tma_ok;  // D >= 64: boxes are 64 channels wide, a partial last block relies on TMA out-of-bounds handling
+  // two-level scan (nseg > 1): the sequence is cut into nseg chunks of whole tiles, scanned by different CTAs
+  int nseg;
+  float *ws_hend;   // (Bp, 2 branches, 2 dirs, nseg, D, 16) chunk-local end state (zero initial state)
+  float *ws_sumdt;  // (Bp, 2, 2, nseg, D)                   sum of dt over the chunk
+  float *ws_h0;     // (Bp, 2, 2, nseg, D, 16)               carried-in state of every chunk (written by scan_carry)
 };
 struct alignas(64) BranchMaps {
   CUtensorMap xz, xdbl, delta, ydir;
@@ -71,7 +76,9 @@ struct TileGeo {
   bool fast;
 };
 
-template <typename T, bool POWER_A>
+// MODE 0: scan with outputs (chunk c > 0 starts from ws_h0).  MODE 1: chunk summary — state only, no C, no y;
+// writes the chunk-local end state and sum(dt) for scan_carry_kernel.
+template <typename T, bool POWER_A, int MODE>
 __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P,
                                                           const __grid_constant__ MaskedMaps M) {
   constexpr int S = ring_stages<T>();
@@ -84,8 +91,11 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   const int tid = threadIdx.x;
   const int d0 = blockIdx.x * kCh;
   const int b = blockIdx.y;
-  const int bi = P.first_branch + (blockIdx.z >> 1);
-  const int k = blockIdx.z & 1;
+  const int nseg = P.nseg;
+  const int seg = blockIdx.z % nseg;
+  const int zi = blockIdx.z / nseg;
+  const int bi = P.first_branch + (zi >> 1);
+  const int k = zi & 1;
   const BranchDev<T> br = P.br[bi];
   const BranchMaps &maps = M.m[bi];
   const int n_sel = br.n_sel, n_tail = br.n_tail;
@@ -93,6 +103,10 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   const int D = P.D, L = P.L;
   const int nch = min(kCh, D - d0);
   const int ntiles = (Lp + kT - 1) / kT;
+  // chunk `seg` owns tiles [t_begin, t_end) in processing order; an empty chunk still reports a zero summary
+  const int seg_tiles = (ntiles + nseg - 1) / nseg;
+  const int t_begin = min(seg * seg_tiles, ntiles), t_end = min(t_begin + seg_tiles, ntiles);
+  const size_t ws_row = ((((size_t)b * 2 + bi) * 2 + k) * nseg + seg) * D + d0;   // + channel
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], kCh);
@@ -137,8 +151,8 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   };
 
   auto issue_load = [&](int t, const TileGeo &g) {
-    Stage<T> &sg = st[t % S];
-    uint64_t *bar = &full_bar[t % S];
+    Stage<T> &sg = st[(t - t_begin) % S];
+    uint64_t *bar = &full_bar[(t - t_begin) % S];
     if (g.fast) {
       if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)sizeof(Stage<T>));
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   auto store_y = [&](int t, const TileGeo &g) {
     if (g.fast) {
       if (tid == 0) {
-        tma_store_3d(&maps.ydir, d0, g.row0, k * P.Bp + b, &ybuf[t & 1][0][0]);
+        tma_store_3d(&maps.ydir, d0, g.row0, k * P.Bp + b, &ybuf[(t - t_begin) & 1][0][0]);
         bulk_commit();
       }
     } else {
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
         const int l = g.l_lo + jj;
         if (l < n_sel) {
           const int row = br.idx_iota ? l : __ldg(br.idx + l);
-          const uint4 v = *reinterpret_cast<const uint4 *>(&ybuf[t & 1][l - g.l_first][w * kPer]);
+          const uint4 v = *reinterpret_cast<const uint4 *>(&ybuf[(t - t_begin) & 1][l - g.l_first][w * kPer]);
           *reinterpret_cast<uint4 *>(ydst + (size_t)row * D + w * kPer) = v;
         }
       }
@@ -197,34 +211,51 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   const int ch = k * D + d0 + (live ? tid : 0);
   ChannelScan<POWER_A> cs;
   cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
+  if (MODE == 0 && seg > 0 && live) {
+    const float *h0 = P.ws_h0 + (ws_row + tid) * kN;
+#pragma unroll
+    for (int j = 0; j < kN / 2; ++j) cs.h[j] = pk(h0[2 * j], h0[2 * j + 1]);
+  }
+  float sumdt = 0.f;
 
-  for (int t = 0; t < min(S - 1, ntiles); ++t) issue_load(t, geo(t));
+  // ring slots and y double-buffer are indexed by the tile number relative to the chunk start
+  for (int t = t_begin; t < min(t_begin + S - 1, t_end); ++t) issue_load(t, geo(t));
 
   TileGeo prev = {};
-  for (int t = 0; t < ntiles; ++t) {
-    const int s = t % S;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int tr = t - t_begin;
+    const int s = tr % S;
     const TileGeo g = geo(t);
-    mbar_wait(&full_bar[s], (t / S) & 1);
+    mbar_wait(&full_bar[s], (tr / S) & 1);
     if (k16) {  // widen this tile's B|C rows to fp32 once per CTA: thread -> (row tid/4, 8 values)
       const int j = tid >> 2, q = (tid & 3) * 8;
       uint4 w = *reinterpret_cast<const uint4 *>(&st[s].bc[j][q]);
       const T *e = reinterpret_cast<const T *>(&w);
       float4 lo = make_float4(IO<T>::ld(e + 0), IO<T>::ld(e + 1), IO<T>::ld(e + 2), IO<T>::ld(e + 3));
       float4 hi = make_float4(IO<T>::ld(e + 4), IO<T>::ld(e + 5), IO<T>::ld(e + 6), IO<T>::ld(e + 7));
-      float4 *dst = reinterpret_cast<float4 *>(&bcf[t & 1][j][q]);
+      float4 *dst = reinterpret_cast<float4 *>(&bcf[tr & 1][j][q]);
       dst[0] = lo;
       dst[1] = hi;
     }
     if (tid == 0) bulk_wait_read<0>();  // the y tile stored two iterations ago has left ybuf[t & 1]
     __syncthreads();                    // B|C published; everyone is done with tile t-1 (its stage and y tile)
-    if (t > 0) store_y(t - 1, prev);
-    if (t + S - 1 < ntiles) issue_load(t + S - 1, geo(t + S - 1));
+    if (MODE == 0 && tr > 0) store_y(t - 1, prev);
+    if (t + S - 1 < t_end) issue_load(t + S - 1, geo(t + S - 1));
 
     if (live) {
       const T *us = &st[s].u[0][tid], *ds = &st[s].dt[0][tid];
-      const float *bcs = k16 ? &bcf[t & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
-      T *ys = &ybuf[t & 1][0][tid];
-      if (g.nrows == kT) {
+      const float *bcs = k16 ? &bcf[tr & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
+      T *ys = &ybuf[tr & 1][0][tid];
+      if (MODE == 1) {
+        for (int r = 0; r < g.nrows; ++r) {
+          const int j = k ? kT - 1 - r : r;
+          const StepIn si = cs.template prologue<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh));
+          uint64_t p[kN / 2];
+          cs.decay(si.dt, p);
+          cs.apply_state(p, si, bcs + j * 2 * kN);
+          sumdt += si.dt;
+        }
+      } else if (g.nrows == kT) {
         // smem row of step r: r (direction 0) or 15 - r (direction 1); kGroup steps are software-pipelined
         if (k == 0) {
 #pragma unroll 1
@@ -261,10 +292,44 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     fence_proxy_async();  // make this thread's ybuf writes visible to the TMA store issued after the next barrier
     prev = g;
   }
+  if (MODE == 1) {
+    if (live) {
+      float *he = P.ws_hend + (ws_row + tid) * kN;
+#pragma unroll
+      for (int j = 0; j < kN / 2; ++j) upk(cs.h[j], he[2 * j], he[2 * j + 1]);
+      P.ws_sumdt[ws_row + tid] = sumdt;
+    }
+    return;
+  }
   if (tid == 0) bulk_wait_read<0>();
   __syncthreads();
-  if (ntiles > 0) store_y(ntiles - 1, prev);
+  if (t_end > t_begin) store_y(t_end - 1, prev);
   if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
+}
+
+// Inter-chunk carry of the two-level scan: one thread per (batch, branch, direction, channel) walks the nseg
+// chunk summaries in processing order:  h0[c+1] = exp(A * sumdt[c]) * h0[c] + hend[c],  h0[0] = 0.
+__global__ void __launch_bounds__(128) scan_carry_kernel(const float *__restrict__ A0, const float *__restrict__ A1,
+                                                         const float *__restrict__ hend, const float *__restrict__ sumdt,
+                                                         float *__restrict__ h0, int Bp, int D, int nseg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // ((b*2 + bi)*2 + k)*D + d
+  if (i >= (long long)Bp * 4 * D) return;
+  const int d = (int)(i % D), k = (int)((i / D) & 1), bi = (int)((i / (2LL * D)) & 1);
+  const float *A = (bi ? A1 : A0);
+  if (!A) return;                                   // branch not live
+  A += ((size_t)k * D + d) * kN;
+  float a[kN], h[kN];
+#pragma unroll
+  for (int n = 0; n < kN; ++n) { a[n] = A[n] * kLog2e; h[n] = 0.f; }
+  const long long base = (i / D) * (long long)nseg * D + d;              // chunk c sits at base + c*D
+  for (int c = 0; c < nseg; ++c) {
+    const size_t row = (size_t)(base + (long long)c * D);
+#pragma unroll
+    for (int n = 0; n < kN; ++n) h0[row * kN + n] = h[n];
+    const float sd = sumdt[row];
+#pragma unroll
+    for (int n = 0; n < kN; ++n) h[n] = fmaf(ex2(a[n] * sd), h[n], hend[row * kN + n]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -305,6 +370,18 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   MaskedMaps M;
   memset(&M, 0, sizeof(M));
   P.Bp = a->Bp; P.L = a->L; P.D = a->D; P.xw = a->xw;
+  const int nseg = a->nseg > 1 ? a->nseg : 1;
+  P.nseg = nseg;
+  P.ws_hend = P.ws_sumdt = P.ws_h0 = nullptr;
+  if (nseg > 1) {
+    const size_t rows = (size_t)a->Bp * 4 * nseg * a->D;
+    if (!a->workspace || a->workspace_bytes < (long long)(rows * (2 * kN + 1) * sizeof(float)))
+      ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg=%d needs a workspace of %lld bytes (actk_masked_scan_workspace_bytes)",
+                nseg, (long long)(rows * (2 * kN + 1) * sizeof(float)));
+    P.ws_hend = static_cast<float *>(a->workspace);
+    P.ws_h0 = P.ws_hend + rows * kN;
+    P.ws_sumdt = P.ws_h0 + rows * kN;
+  }
   // boxes are always 64 channels wide; a last partial channel block relies on TMA's out-of-bounds handling
   // (zero fill on load, clipping on store), so any D >= 64 qualifies (channel-sharded slices such as D/8 = 80)
   P.tma_ok = (a->D >= kCh) ? 1 : 0;
@@ -336,11 +413,21 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     int j = i + 1;
     while (j < a->n_branches && a->br[j].n_sel > 0 && a->br[j].a_kind == a->br[i].a_kind) ++j;
     P.first_branch = i;
-    dim3 grid((a->D + kCh - 1) / kCh, a->Bp, 2 * (j - i));
-    if (a->br[i].a_kind == ACTK_A_POWER)
-      masked_scan_kernel<T, true><<<grid, kCh, 0, stream>>>(P, M);
-    else
-      masked_scan_kernel<T, false><<<grid, kCh, 0, stream>>>(P, M);
+    dim3 grid((a->D + kCh - 1) / kCh, a->Bp, 2 * (j - i) * nseg);
+    const bool pw = a->br[i].a_kind == ACTK_A_POWER;
+    if (nseg > 1) {   // level 1: chunk summaries; level 2: carries; then the scan proper starts every chunk from its carry
+      if (pw) masked_scan_kernel<T, true, 1><<<grid, kCh, 0, stream>>>(P, M);
+      else masked_scan_kernel<T, false, 1><<<grid, kCh, 0, stream>>>(P, M);
+      ACTK_CUDA_OK(cudaGetLastError());
+      const float *A0 = (i == 0) ? a->br[0].A : nullptr;
+      const float *A1 = (i <= 1 && j >= 2) ? a->br[1].A : nullptr;
+      const long long n = (long long)a->Bp * 4 * a->D;
+      scan_carry_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(A0, A1, P.ws_hend, P.ws_sumdt, P.ws_h0, a->Bp,
+                                                                          a->D, nseg);
+      ACTK_CUDA_OK(cudaGetLastError());
+    }
+    if (pw) masked_scan_kernel<T, true, 0><<<grid, kCh, 0, stream>>>(P, M);
+    else masked_scan_kernel<T, false, 0><<<grid, kCh, 0, stream>>>(P, M);
     ACTK_CUDA_OK(cudaGetLastError());
     i = j;
   }
@@ -353,6 +440,11 @@ static bool misaligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) &
 
 using namespace actk;
 
+extern "C" long long actk_masked_scan_workspace_bytes(const actk_masked_scan_args *a) {
+  if (!a || a->nseg <= 1) return 0;
+  return (long long)a->Bp * 4 * a->nseg * a->D * (2 * kN + 1) * (long long)sizeof(float);
+}
+
 extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream) {
   if (!a) ACTK_FAIL(ACTK_ERR_BAD_ARG, "actk_masked_scan_fwd: args is NULL");
   if (a->dtype < ACTK_F32 || a->dtype > ACTK_BF16) ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "masked_scan: dtype=%d", a->dtype);
@@ -361,6 +453,7 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
   if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->xw < 4 * kN)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d L=%d D=%d xw=%d", a->Bp, a->L, a->D, a->xw);
   if (a->Bp > 32767) ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d exceeds grid.y / 2", a->Bp);
+  if (a->nseg < 0 || a->nseg > 4096) ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg=%d (0/1 = single level, <= 4096)", a->nseg);
   const int es = a->dtype == ACTK_F32 ? 4 : 2;
   if ((a->D * es) % 16 != 0)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: D=%d must be a multiple of %d (16-byte channel rows)", a->D, 16 / es);

@@ -114,6 +114,18 @@ struct ChannelScan {
     return fmaf(dskip, s.u, y0 + y1);
   }
 
+  // State-only update (no C, no y): the chunk-summary pass of the two-level scan.
+  __device__ __forceinline__ void apply_state(const uint64_t (&p)[kN / 2], const StepIn &s, const float *__restrict__ bc) {
+    uint64_t x2 = pk(s.x, s.x);
+    const ulonglong2 *bc2 = reinterpret_cast<const ulonglong2 *>(bc);
+#pragma unroll
+    for (int q = 0; q < kN / 4; ++q) {
+      ulonglong2 Bq = bc2[q];
+      h[2 * q] = fma2(p[2 * q], h[2 * q], mul2(x2, Bq.x));
+      h[2 * q + 1] = fma2(p[2 * q + 1], h[2 * q + 1], mul2(x2, Bq.y));
+    }
+  }
+
   // Unpipelined convenience form (operator-contract kernel, ragged tails).
   template <bool SOFTPLUS>
   __device__ __forceinline__ float step(float u, float delta_raw, const float *__restrict__ bc) {

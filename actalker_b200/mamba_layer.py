@@ -166,6 +166,19 @@ class SS2D_Unit(nn.Module):
         return self.forward_core(input)
 
 
+SCAN_SEGMENTS = None   # None: choose per call (auto_segments); an int forces that many chunks (tests, tuning)
+
+
+def auto_segments(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
+    """Chunks per sequence for the two-level scan.  One chunk (single level, no extra work) whenever the
+    independent (batch x branch x direction x channel-block) axes already give every SM ~4 CTAs; otherwise cut time
+    so that about 6 CTAs per SM exist, keeping chunks >= 8 tiles (128 steps) so the 75 % extra state-only pass and
+    the carry stay a small price for the parallelism (BASELINE config 5, single-frame calls)."""
+    if n_ctas >= 4 * n_sms or min_tiles < 16:
+        return 1
+    return max(1, min(-(-6 * n_sms // n_ctas), min_tiles // 8))
+
+
 def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None, ch_slice=None):
     """Shared launcher: x_proj / dt_proj GEMMs (cuBLAS) + one actk_masked_scan_fwd for all given branches.
     xzs[i]: (Bp, L, D) contiguous; tails[i]: (Bp, n_tail, D) or None; idxs[i]: int32 (n_sel,).
@@ -220,7 +233,17 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz_k), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
         b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(A), _ptr(Dsk), _ptr(dtb), _ptr(ydir)
         keep += [xdbl, xdbl_tail, delta, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
-    if any(n > 0 for n in n_sels):
+    live = [i for i, n in enumerate(n_sels) if n > 0]
+    if live:
+        min_tiles = min(-(-(n_sels[i] + (0 if tails[i] is None else tails[i].shape[1])) // 16) for i in live)
+        n_ctas = -(-Dk // 64) * Bp * 2 * len(live)
+        args.nseg = SCAN_SEGMENTS if SCAN_SEGMENTS is not None else auto_segments(n_ctas, min_tiles)
+        ws_bytes = lib.actk_masked_scan_workspace_bytes(ct.byref(args))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
+            args.workspace, args.workspace_bytes = ws.data_ptr(), ws_bytes
+            keep.append(ws)
+    if live:
         with torch.cuda.device(x0.device), _timed("masked_scan", x0.device):
             _lib.check(lib.actk_masked_scan_fwd(ct.byref(args), _stream(x0)), "actk_masked_scan_fwd")
     return outs

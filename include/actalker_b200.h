@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 2
+#define ACTK_ABI_VERSION 3
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -120,9 +120,19 @@ typedef struct {
   int n_branches; /* 1 or 2 */
   int Bp, L, D, N, xw;
   int dtype; /* actk_dtype of xz/tail/xdbl/delta/ydir */
+  /* Two-level scan for small batches / long sequences (BASELINE config 5: one 518k-token sequence): with
+   * nseg > 1 every sequence is cut into nseg chunks of whole 16-step tiles that different CTAs scan
+   * concurrently — level 1 computes each chunk's end state from a zero start and its sum(dt), a carry kernel
+   * chains h0[c+1] = exp(A*sumdt[c])*h0[c] + hend[c], level 2 rescans every chunk from its carried-in state and
+   * produces y.  nseg <= 1: single level, no workspace.  Results equal the single-level scan up to fp32
+   * re-association. */
+  int nseg;
+  void *workspace;            /* device, >= actk_masked_scan_workspace_bytes(args) when nseg > 1 */
+  long long workspace_bytes;
 } actk_masked_scan_args;
 
 int actk_masked_scan_fwd(const actk_masked_scan_args *args, void *stream);
+long long actk_masked_scan_workspace_bytes(const actk_masked_scan_args *args); /* host helper, 0 when nseg <= 1 */
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Direction merge + branch sum + LayerNorm — mamba_layer.py:1542-1547 (y_fwd + flip(y_bwd)),
