@@ -31,6 +31,7 @@ void set_error(const char *fmt, ...);
 template <typename T> struct IO;
 template <> struct IO<float> {
   static __device__ __forceinline__ float ld(const float *p) { return *p; }
+  static __device__ __forceinline__ float f(float v) { return v; }
   static __device__ __forceinline__ float rnd(float v) { return v; }
   static __device__ __forceinline__ void st(float *p, float v) { *p = v; }
   // two adjacent elements (8-byte aligned)
@@ -44,6 +45,7 @@ template <> struct IO<float> {
 };
 template <> struct IO<__half> {
   static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
+  static __device__ __forceinline__ float f(__half v) { return __half2float(v); }
   static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
   static __device__ __forceinline__ void st(__half *p, float v) { *p = __float2half_rn(v); }
   static __device__ __forceinline__ void ld2(const __half *p, float &a, float &b) {
@@ -58,6 +60,7 @@ template <> struct IO<__nv_bfloat16> {
   static __device__ __forceinline__ float ld(const __nv_bfloat16 *p) {
     return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t *>(p)) << 16);
   }
+  static __device__ __forceinline__ float f(__nv_bfloat16 v) { return __bfloat162float(v); }
   static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
   static __device__ __forceinline__ void st(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
   static __device__ __forceinline__ void ld2(const __nv_bfloat16 *p, float &a, float &b) {
