@@ -11,7 +11,7 @@ def main():
     for dtype in (torch.bfloat16, torch.float32):
         for Lp in (5217, 5186):
             g = torch.Generator(device=dev).manual_seed(0)
-            B, Dm = 25, 1280
+            B, Dm = int(os.environ.get("OPB", "25")), 1280
             u = torch.randn(B, Dm, Lp, device=dev, generator=g).to(dtype)
             delta = torch.randn(B, Dm, Lp, device=dev, generator=g).to(dtype)
             A = -torch.exp(torch.randn(Dm, 16, device=dev, generator=g))
