@@ -246,6 +246,12 @@ def run_ours(args, rank, world, local_rank):
     extra = {k: statistics.mean(v) for k, v in kern.items() if k not in ("masked_scan", "merge_ln")}
     achieved = q / (scan_ms * 1e-3) / 1e9
     updates = Bp * (2 * L + 35) * 2 * D * 16
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (Bp, d_model, args.dtype) == (25, 320, "bf16") and not channel:
+        with open(tpath) as f:
+            ent = json.load(f).get("masked_scan config2 bf16 " + {0: "general", 1: "power"}[a_kind])
+        traffic = ent["bytes"] if ent else None
     cb = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
@@ -265,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
                                    "all-gather of the merged slices before out_norm/out_proj") if channel else
                                   f"batch-sharded x{world} (each rank its own B'={Bp} frames), no collective"},
         "roofline": {"bound": "hbm", "kernel": "masked_scan_kernel (actk_masked_scan_fwd)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": q, "kernel_ms": scan_ms, "state_updates_per_s": updates / (scan_ms * 1e-3),
                      "merge_ln_ms": merge_ms, "kernel_share_of_step": scan_ms / ms_step,
                      **{k + "_ms": v for k, v in extra.items()}},
