@@ -9,5 +9,7 @@ hand-written CUDA kernels behind the C-ABI declared in include/actalker_b200.h. 
 from .selective_scan_interface import MAMBA_AVAILABLE, a_kind_of, selective_scan_fn  # noqa: F401
 from .mamba_layer import SS2D_Unit, SS2D_cond_v10  # noqa: F401
 from .mask import MaskIndexCache, downsample, mask_to_index  # noqa: F401
+from .host_api import HostStreamedLayer  # noqa: F401
+from .sharded import ShardPlan, ShardedSS2DCondV10  # noqa: F401
 
 __version__ = "0.1.0"

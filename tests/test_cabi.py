@@ -112,3 +112,21 @@ def test_cpu_tensors_are_refused_loudly():
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
         layer(torch.randn(1, 64, 32), torch.randn(1, 1, 64), torch.randn(1, 33, 64),
               [torch.ones(1, 1, 64, 64), torch.ones(1, 1, 64, 64)])
+
+
+def test_workspace_and_gathered_layernorm_validation():
+    lib = _lib.load()
+    m = _lib.MaskedScanArgs()
+    m.Bp, m.D, m.nseg = 1, 640, 1
+    assert lib.actk_masked_scan_workspace_bytes(C.byref(m)) == 0
+    m.nseg = 23
+    assert lib.actk_masked_scan_workspace_bytes(C.byref(m)) == 1 * 4 * 23 * 640 * 33 * 4
+    m.dtype, m.n_branches, m.N, m.L, m.xw = _lib.ACTK_BF16, 1, 16, 64, 104
+    m.nseg = 5000
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_ARG")
+    assert lib.actk_gathered_layernorm_fwd(None, 2, 10, 64, None, None, 1e-5, None, _lib.ACTK_BF16, None) \
+        == _status("ACTK_ERR_BAD_ARG")
+    assert lib.actk_gathered_layernorm_fwd(1 << 20, 2, 10, 60, 1 << 20, 1 << 20, 1e-5, 1 << 20, _lib.ACTK_BF16, None) \
+        == _status("ACTK_ERR_BAD_SHAPE")           # Ds % 8
+    assert lib.actk_gathered_layernorm_fwd(1 << 20, 2, 10, 64, 1 << 20, 1 << 20, 1e-5, 1 << 20, 9, None) \
+        == _status("ACTK_ERR_BAD_DTYPE")

@@ -7,7 +7,7 @@
 #include <vector>
 
 #include "../actalker_b200/csrc/scan_core.cuh"
-#include "../actalker_b200/csrc/scan_core2.cuh"
+#include "scan_core2.cuh"
 
 namespace actk {
 void set_error(const char *, ...) {}

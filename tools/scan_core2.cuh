@@ -1,3 +1,5 @@
+// EXPERIMENT (not part of the product library): evaluated in tools/microbench_step.cu and as a one-warp-per-CTA kernel
+// on B200; see DESIGN.md §4.1 "what was tried".  Kept so the microbenchmark stays reproducible.
 // Two-channels-per-thread form of the selective-scan recurrence (see scan_core.cuh for the math).
 //
 // Why two: with one channel per thread every step pulls the 32 B|C values of the step (128 B) into each lane's
@@ -8,7 +10,7 @@
 // register feed both channels through the scalar-broadcast operand of FMUL2/FFMA2, halving the LDS traffic per
 // channel-step, and turns u / delta / y accesses into 32-bit bf16x2 words.
 #pragma once
-#include "common.cuh"
+#include "../actalker_b200/csrc/common.cuh"
 
 namespace actk {
 
