@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
@@ -44,7 +44,7 @@ class BranchArgs(C.Structure):
 class MaskedScanArgs(C.Structure):
     _fields_ = [("br", BranchArgs * 2), ("n_branches", _i),
                 ("Bp", _i), ("L", _i), ("D", _i), ("N", _i), ("xw", _i), ("dtype", _i),
-                ("nseg", _i), ("workspace", _vp), ("workspace_bytes", _ll)]
+                ("nseg", _i), ("workspace", _vp), ("workspace_bytes", _ll), ("chain_chunks", _i)]
 
 
 class MergeLnArgs(C.Structure):

@@ -53,6 +53,11 @@ struct MaskedParams {
   float *ws_hend;   // (Bp, 2 branches, 2 dirs, nseg, D, 16) chunk-local end state (zero initial state)
   float *ws_sumdt;  // (Bp, 2, 2, nseg, D)                   sum of dt over the chunk
   float *ws_h0;     // (Bp, 2, 2, nseg, D, 16)               carried-in state of every chunk (written by scan_carry)
+  // chain mode (MODE 2): nseg chunks of a sequence run one after another on whichever CTA slot frees up first
+  int nq, nblk;       // sequences (= CTAs of a single-level launch) and channel blocks per (batch, item)
+  int *chain_ctr;     // [1]   work counter, zeroed before launch
+  int *chain_flag;    // [nq]  number of finished chunks of sequence q, zeroed before launch
+  float *chain_state; // [nq][64][16] state handed from chunk c to chunk c+1
 };
 struct alignas(64) BranchMaps {
   CUtensorMap xz, xdbl, delta, ydir;
@@ -78,6 +83,13 @@ struct TileGeo {
 
 // MODE 0: scan with outputs (chunk c > 0 starts from ws_h0).  MODE 1: chunk summary — state only, no C, no y;
 // writes the chunk-local end state and sum(dt) for scan_carry_kernel.
+// MODE 2: chained chunks.  2000 warp-sequences on 592 warp schedulers cannot be balanced statically (3 or 4 warps
+// per scheduler; the 4-warp ones set the pace of a single-level launch).  Here every sequence is cut into nseg
+// sequentially dependent chunks; a 1-D grid of nq*nseg CTAs draws (chunk, sequence) work items from an atomic
+// counter in chunk-major order, waits (acquire) until the previous chunk of its sequence has published its state,
+// scans, and publishes (release).  Chunks of one sequence land on different SMs, so every sequence advances at the
+// average rate and fast SMs simply take more items.  A waiting CTA only ever waits for a CTA that drew a smaller
+// ticket, i.e. one that is already running: no deadlock whatever the hardware's dispatch order.
 template <typename T, bool POWER_A, int MODE>
 __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P,
                                                           const __grid_constant__ MaskedMaps M) {
@@ -89,11 +101,23 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   __shared__ alignas(8) uint64_t full_bar[S];
 
   const int tid = threadIdx.x;
-  const int d0 = blockIdx.x * kCh;
-  const int b = blockIdx.y;
   const int nseg = P.nseg;
-  const int seg = blockIdx.z % nseg;
-  const int zi = blockIdx.z / nseg;
+  int bx, b, zi, seg, q = 0;
+  if (MODE == 2) {
+    __shared__ int ticket;
+    if (tid == 0) ticket = atomicAdd(P.chain_ctr, 1);
+    __syncthreads();
+    seg = ticket / P.nq;
+    q = ticket - seg * P.nq;
+    bx = q % P.nblk;
+    b = (q / P.nblk) % P.Bp;
+    zi = q / (P.nblk * P.Bp);
+  } else {
+    bx = blockIdx.x; b = blockIdx.y;
+    seg = blockIdx.z % nseg;
+    zi = blockIdx.z / nseg;
+  }
+  const int d0 = bx * kCh;
   const int bi = P.first_branch + (zi >> 1);
   const int k = zi & 1;
   const BranchDev<T> br = P.br[bi];
@@ -216,6 +240,23 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
 #pragma unroll
     for (int j = 0; j < kN / 2; ++j) cs.h[j] = pk(h0[2 * j], h0[2 * j + 1]);
   }
+  if (MODE == 2 && seg > 0) {
+    if (tid == 0) {   // acquire: the previous chunk of this sequence has published its state
+      int done;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(P.chain_flag + q) : "memory");
+        if (done < seg) __nanosleep(200);
+      } while (done < seg);
+    }
+    __syncthreads();
+    const float4 *h0 = reinterpret_cast<const float4 *>(P.chain_state + ((size_t)q * kCh + tid) * kN);
+#pragma unroll
+    for (int j = 0; j < kN / 4; ++j) {
+      const float4 v = __ldcg(h0 + j);
+      cs.h[2 * j] = pk(v.x, v.y);
+      cs.h[2 * j + 1] = pk(v.z, v.w);
+    }
+  }
   float sumdt = 0.f;
 
   // ring slots and y double-buffer are indexed by the tile number relative to the chunk start
@@ -239,7 +280,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     }
     if (tid == 0) bulk_wait_read<0>();  // the y tile stored two iterations ago has left ybuf[t & 1]
     __syncthreads();                    // B|C published; everyone is done with tile t-1 (its stage and y tile)
-    if (MODE == 0 && tr > 0) store_y(t - 1, prev);
+    if (MODE != 1 && tr > 0) store_y(t - 1, prev);
     if (t + S - 1 < t_end) issue_load(t + S - 1, geo(t + S - 1));
 
     if (live) {
@@ -301,8 +342,21 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     }
     return;
   }
+  if (MODE == 2 && seg + 1 < nseg) {   // publish the state for the next chunk of this sequence (release)
+    float4 *hs = reinterpret_cast<float4 *>(P.chain_state + ((size_t)q * kCh + tid) * kN);
+#pragma unroll
+    for (int j = 0; j < kN / 4; ++j) {
+      float4 v;
+      upk(cs.h[2 * j], v.x, v.y);
+      upk(cs.h[2 * j + 1], v.z, v.w);
+      __stcg(hs + j, v);
+    }
+    __threadfence();
+  }
   if (tid == 0) bulk_wait_read<0>();
   __syncthreads();
+  if (MODE == 2 && seg + 1 < nseg && tid == 0)
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.chain_flag + q), "r"(seg + 1) : "memory");
   if (t_end > t_begin) store_y(t_end - 1, prev);
   if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
 }
@@ -373,6 +427,9 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   const int nseg = a->nseg > 1 ? a->nseg : 1;
   P.nseg = nseg;
   P.ws_hend = P.ws_sumdt = P.ws_h0 = nullptr;
+  P.chain_ctr = P.chain_flag = nullptr; P.chain_state = nullptr; P.nq = P.nblk = 0;
+  const bool chain = a->chain_chunks > 1;
+  if (chain && a->nseg > 1) ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg and chain_chunks are mutually exclusive");
   if (nseg > 1) {
     const size_t rows = (size_t)a->Bp * 4 * nseg * a->D;
     if (!a->workspace || a->workspace_bytes < (long long)(rows * (2 * kN + 1) * sizeof(float)))
@@ -415,6 +472,25 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     P.first_branch = i;
     dim3 grid((a->D + kCh - 1) / kCh, a->Bp, 2 * (j - i) * nseg);
     const bool pw = a->br[i].a_kind == ACTK_A_POWER;
+    if (chain) {
+      P.nblk = (a->D + kCh - 1) / kCh;
+      P.nq = P.nblk * a->Bp * 2 * (j - i);
+      P.nseg = a->chain_chunks;
+      const size_t state_bytes = (size_t)P.nq * kCh * kN * sizeof(float);
+      const size_t need = state_bytes + ((size_t)P.nq + 1) * sizeof(int);
+      if (!a->workspace || (size_t)a->workspace_bytes < need)
+        ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: chain_chunks=%d needs a workspace of %zu bytes", a->chain_chunks, need);
+      P.chain_state = static_cast<float *>(a->workspace);
+      P.chain_flag = reinterpret_cast<int *>(static_cast<char *>(a->workspace) + state_bytes);
+      P.chain_ctr = P.chain_flag + P.nq;
+      ACTK_CUDA_OK(cudaMemsetAsync(P.chain_flag, 0, ((size_t)P.nq + 1) * sizeof(int), stream));
+      const unsigned nblocks = (unsigned)P.nq * a->chain_chunks;
+      if (pw) masked_scan_kernel<T, true, 2><<<nblocks, kCh, 0, stream>>>(P, M);
+      else masked_scan_kernel<T, false, 2><<<nblocks, kCh, 0, stream>>>(P, M);
+      ACTK_CUDA_OK(cudaGetLastError());
+      i = j;
+      continue;
+    }
     if (nseg > 1) {   // level 1: chunk summaries; level 2: carries; then the scan proper starts every chunk from its carry
       if (pw) masked_scan_kernel<T, true, 1><<<grid, kCh, 0, stream>>>(P, M);
       else masked_scan_kernel<T, false, 1><<<grid, kCh, 0, stream>>>(P, M);
@@ -441,7 +517,12 @@ static bool misaligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) &
 using namespace actk;
 
 extern "C" long long actk_masked_scan_workspace_bytes(const actk_masked_scan_args *a) {
-  if (!a || a->nseg <= 1) return 0;
+  if (!a) return 0;
+  if (a->chain_chunks > 1) {   // state of every sequence-CTA + flags + counter (sized for both branches in one launch)
+    const long long nq = (long long)((a->D + kCh - 1) / kCh) * a->Bp * 4;
+    return nq * kCh * kN * (long long)sizeof(float) + (nq + 1) * (long long)sizeof(int);
+  }
+  if (a->nseg <= 1) return 0;
   return (long long)a->Bp * 4 * a->nseg * a->D * (2 * kN + 1) * (long long)sizeof(float);
 }
 
@@ -453,6 +534,8 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
   if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->xw < 4 * kN)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d L=%d D=%d xw=%d", a->Bp, a->L, a->D, a->xw);
   if (a->Bp > 32767) ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: Bp=%d exceeds grid.y / 2", a->Bp);
+  if (a->chain_chunks < 0 || a->chain_chunks > 1024)
+    ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: chain_chunks=%d (0/1 = off, <= 1024)", a->chain_chunks);
   if (a->nseg < 0 || a->nseg > 4096) ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg=%d (0/1 = single level, <= 4096)", a->nseg);
   const int es = a->dtype == ACTK_F32 ? 4 : 2;
   if ((a->D * es) % 16 != 0)

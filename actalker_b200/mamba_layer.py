@@ -167,6 +167,17 @@ class SS2D_Unit(nn.Module):
 
 
 SCAN_SEGMENTS = None   # None: choose per call (auto_segments); an int forces that many chunks (tests, tuning)
+SCAN_CHAIN = None      # None: choose per call (auto_chain); an int forces that many chained chunks (0/1 = off)
+POISON_OUTPUTS = False # tests: pre-fill the scan output with NaN so a row the kernel fails to write cannot go unnoticed
+
+
+def auto_chain(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
+    """Chained chunks per sequence (load balancing, masked_scan.cu MODE 2): worthwhile once the launch fills the
+    GPU (>= 4 CTAs per SM) and sequences are long enough to cut into chunks of >= 40 tiles."""
+    if n_ctas < 4 * n_sms or min_tiles < 80:
+        return 0
+    return min(min_tiles // 40, 64)
+
 
 
 def auto_segments(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
@@ -205,6 +216,8 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         xz, tail, n_sel = xzs[i], tails[i], n_sels[i]
         n_tail = 0 if tail is None else tail.shape[1]
         ydir = torch.empty((2, Bp, L, Dk), dtype=xz.dtype, device=xz.device)
+        if POISON_OUTPUTS:
+            ydir.fill_(float("nan"))
         xz_k = xz[..., lo:hi].contiguous() if sliced else xz
         outs.append((ydir, xz_k))
         b = args.br[i]
@@ -238,6 +251,8 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         min_tiles = min(-(-(n_sels[i] + (0 if tails[i] is None else tails[i].shape[1])) // 16) for i in live)
         n_ctas = -(-Dk // 64) * Bp * 2 * len(live)
         args.nseg = SCAN_SEGMENTS if SCAN_SEGMENTS is not None else auto_segments(n_ctas, min_tiles)
+        if args.nseg <= 1:
+            args.chain_chunks = SCAN_CHAIN if SCAN_CHAIN is not None else auto_chain(n_ctas, min_tiles)
         ws_bytes = lib.actk_masked_scan_workspace_bytes(ct.byref(args))
         if ws_bytes:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)

@@ -163,6 +163,8 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if args.chain is not None:
+        ml.SCAN_CHAIN = args.chain
     dtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.dtype]
     es = 4 if dtype == torch.float32 else 2
     d_model, side = args.d_model, int(72 / (args.d_model / 320))
@@ -307,6 +309,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--params", default="init", choices=["init", "trained", "s4d"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain", type=int, default=None, help="force the number of chained chunks (tuning)")
     ap.add_argument("--shard", default="batch", choices=["batch", "channel"],
                     help="N>1: batch = weak scaling, no collective (default); channel = strong scaling of one call "
                          "with the NCCL all-gather before out_norm")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 3
+#define ACTK_ABI_VERSION 4
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -127,8 +127,13 @@ typedef struct {
    * produces y.  nseg <= 1: single level, no workspace.  Results equal the single-level scan up to fp32
    * re-association. */
   int nseg;
-  void *workspace;            /* device, >= actk_masked_scan_workspace_bytes(args) when nseg > 1 */
+  void *workspace;            /* device, >= actk_masked_scan_workspace_bytes(args) when nseg > 1 or chain_chunks > 1 */
   long long workspace_bytes;
+  /* Load balancing for large launches: with chain_chunks > 1 every sequence is cut into that many sequentially
+   * dependent chunks which a 1-D grid of CTAs draws from an atomic work counter (chunk-major); the state is
+   * handed over through the workspace with release/acquire flags.  Same arithmetic in the same order as the
+   * single-level scan (bit-identical results); mutually exclusive with nseg > 1. */
+  int chain_chunks;
 } actk_masked_scan_args;
 
 int actk_masked_scan_fwd(const actk_masked_scan_args *args, void *stream);

@@ -47,3 +47,17 @@ def load_golden(name):
 
 
 LAYER_CASES = ["layer_ones_f32", "layer_rect_f32", "layer_zero_soft_f32", "layer_ones_bf16", "layer_rect_f16"]
+
+
+@pytest.fixture(autouse=True)
+def _poison_scan_outputs():
+    """Every test runs with the scan output pre-filled with NaN: rows the kernels must write but do not would
+    otherwise be masked by the caching allocator handing back a block that still holds an earlier, correct result."""
+    try:
+        from actalker_b200 import mamba_layer as ml
+    except Exception:
+        yield
+        return
+    ml.POISON_OUTPUTS = True
+    yield
+    ml.POISON_OUTPUTS = False

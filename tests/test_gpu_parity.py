@@ -339,3 +339,40 @@ def test_small_batch_long_sequence_picks_two_level_scan_and_matches_oracle():
         want = ref(x.clone(), idm, cd, [ones, ones])
         got = ours(x.cuda(), idm.cuda(), cd.cuda(), [ones.cuda(), ones.cuda()])
     close(got, want, torch.float32, tol=LAYER_TOL, what="two-level auto")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("chunks", [2, 5])
+def test_chained_chunks_are_bit_identical_to_single_level(dtype, chunks):
+    """Chain mode hands the fp32 state from chunk to chunk unchanged and performs the same operations in the same
+    order, so the result must be bit-identical to the single-level scan (both directions, ragged tiles, masks)."""
+    from actalker_b200 import SS2D_cond_v10, mamba_layer as ml
+    torch.manual_seed(6)
+    side = 24
+    layer = SS2D_cond_v10(d_model=96, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=side,
+                          scan_type="sweep", num_direction=2).eval()
+    with torch.no_grad():
+        layer.audio_unit.A_logs.add_(0.4 * torch.randn_like(layer.audio_unit.A_logs))
+    if dtype != torch.float32:
+        layer = layer.to(dtype)
+        for n, p in layer.named_parameters():
+            if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias")):
+                p.data = p.data.float()
+    layer = layer.cuda()
+    Bp, L = 3, side * side
+    x = torch.randn(Bp, L, 96, device="cuda").to(dtype)
+    idm = torch.randn(Bp, 1, 64, device="cuda").to(dtype)
+    cd = torch.randn(Bp, 33, 64, device="cuda").to(dtype)
+    rect = torch.zeros(1, 1, 192, 192, device="cuda", dtype=dtype)
+    rect[:, :, 24:170, 16:150] = 1
+    masks = [torch.ones(1, 1, 192, 192, device="cuda", dtype=dtype), rect]
+    try:
+        with torch.no_grad():
+            ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = 1, 0
+            want = layer(x, idm, cd, masks)
+            ml.SCAN_CHAIN = chunks
+            got = [layer(x, idm, cd, masks) for _ in range(3)]
+    finally:
+        ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = None, None
+    for g in got:
+        assert torch.equal(g, want)
