@@ -30,8 +30,11 @@ namespace actk {
 constexpr int kCh = 64;  // channels per CTA == threads per CTA
 constexpr int kT = 16;   // time steps per tile
 constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::run)
+#ifndef ACTK_STAGES16
+#define ACTK_STAGES16 4
+#endif
 template <typename T>
-constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : 4; }
+constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : ACTK_STAGES16; }
 
 template <typename T>
 struct BranchDev {

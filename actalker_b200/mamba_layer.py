@@ -173,10 +173,12 @@ POISON_OUTPUTS = False # tests: pre-fill the scan output with NaN so a row the k
 
 def auto_chain(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
     """Chained chunks per sequence (load balancing, masked_scan.cu MODE 2): worthwhile once the launch fills the
-    GPU (>= 4 CTAs per SM) and sequences are long enough to cut into chunks of >= 40 tiles."""
+    GPU (>= 4 CTAs per SM) and sequences are long enough to cut into chunks of ~20 tiles (measured on B200 at
+    config 2, scan ms for 0/4/8/16/24/40 chunks: 1.79/1.60/1.51/1.49/1.50/1.53 general, 1.52/1.31/1.23/1.21/1.22/1.26
+    power)."""
     if n_ctas < 4 * n_sms or min_tiles < 80:
         return 0
-    return min(min_tiles // 40, 64)
+    return min(min_tiles // 20, 64)
 
 
 
