@@ -276,13 +276,15 @@ def run_ours(args, rank, world, local_rank):
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": q, "kernel_ms": scan_ms, "state_updates_per_s": updates / (scan_ms * 1e-3),
                      "merge_ln_ms": merge_ms, "kernel_share_of_step": scan_ms / ms_step,
-                     # The scan is instruction-bound, not HBM-bound, at d_state 16: per 32 channel-steps
-                     # the mix needs 19 MUFU x 8.1 = ~154 SMSP-cycles (general A; measured saturation 170) or, for the
-                     # S4D power path, saturates at 117 (tools/microbench_step.cu, profiles/r01_microbench.txt).
+                     # The scan is instruction-bound, not HBM-bound, at d_state 16.  General A: 19 MUFU
+                     # ops per channel-step x 8.1 SMSP-cycles each (measured MUFU.EX2 rate) = 154 cycles per warp-step,
+                     # a hard floor of this formulation.  S4D power path: the instruction mix saturates at 117 cycles
+                     # per warp-step at any occupancy (tools/microbench_step.cu, profiles/r01_microbench.txt).
                      "instruction_floor": {
-                         "smsp_cycles_per_warp_step": {0: 170.0, 1: 117.0}[a_kind],
-                         "ms": (updates / 16 / 32) * {0: 170.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3,
-                         "source": "profiles/r01_microbench.txt (measured at 1965 MHz, any occupancy >= 32 warps/SM)"},
+                         "smsp_cycles_per_warp_step": {0: 154.0, 1: 117.0}[a_kind],
+                         "ms": (updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3,
+                         "frac_of_floor": ((updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3) / scan_ms,
+                         "source": "profiles/r01_microbench.txt (B200 at 1965 MHz)"},
                      **{k + "_ms": v for k, v in extra.items()}},
         "e2e": {"value": tokens / (ms_e2e * 1e-3) / 1e9, "unit": "Gtokens/s",
                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (hx, hid, hcd)),
