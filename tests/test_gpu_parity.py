@@ -376,3 +376,34 @@ def test_chained_chunks_are_bit_identical_to_single_level(dtype, chunks):
         ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = None, None
     for g in got:
         assert torch.equal(g, want)
+
+
+@pytest.mark.parametrize("cfg", [(64, 12, 2, torch.float32), (320, 18, 4, torch.bfloat16), (320, 72, 25, torch.bfloat16)])
+def test_layer_is_cuda_graph_capturable(cfg):
+    """After the caches are warm a layer call has static shapes and no host sync: capture it (tensor maps, chain-mode
+    memset and all) and replay with new input contents; results must equal eager calls bit for bit."""
+    from actalker_b200 import SS2D_cond_v10
+    from actalker_b200.graphed import GraphedLayer
+    d_model, side, Bp, dtype = cfg
+    torch.manual_seed(13)
+    layer = SS2D_cond_v10(d_model=d_model, d_cond=128, cond_size=32, dropout=0.1, d_state=16, size=side,
+                          scan_type="sweep", num_direction=2).eval()
+    if dtype != torch.float32:
+        layer = layer.to(dtype)
+        for n, p in layer.named_parameters():
+            if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias")):
+                p.data = p.data.float()
+    layer = layer.cuda()
+    L = side * side
+    mk = lambda: (torch.randn(Bp, L, d_model, device="cuda").to(dtype), torch.randn(Bp, 1, 128, device="cuda").to(dtype),
+                  torch.randn(Bp, 33, 128, device="cuda").to(dtype))
+    rect = torch.zeros(1, 1, side * 8, side * 8, device="cuda", dtype=dtype)
+    rect[:, :, side: 7 * side, 2 * side: 6 * side] = 1
+    masks = [torch.ones_like(rect), rect]
+    g = GraphedLayer(layer, *mk(), masks)
+    for _ in range(3):
+        x, idm, cd = mk()
+        got = g(x, idm, cd).clone()
+        with torch.no_grad():
+            want = layer(x, idm, cd, masks)
+        assert torch.equal(got, want)
