@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
@@ -37,7 +37,7 @@ class ScanArgs(C.Structure):
 
 class BranchArgs(C.Structure):
     _fields_ = [("xz", _vp), ("tail", _vp), ("xdbl", _vp), ("xdbl_tail", _vp), ("delta", _vp),
-                ("idx", _vp), ("A", _vp), ("Dskip", _vp), ("dt_bias", _vp), ("ydir", _vp),
+                ("delta_tail", _vp), ("idx", _vp), ("A", _vp), ("Dskip", _vp), ("dt_bias", _vp), ("ydir", _vp),
                 ("n_sel", _i), ("n_tail", _i), ("a_kind", _i)]
 
 

@@ -38,7 +38,7 @@ constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : ACTK_STAGES16; }
 
 template <typename T>
 struct BranchDev {
-  const T *xz, *tail, *xdbl, *xdbl_tail, *delta;
+  const T *xz, *tail, *xdbl, *xdbl_tail, *delta, *delta_tail;
   const int *idx;
   const float *A, *Dskip, *dt_bias;
   T *ydir;
@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
           src_rows(l, usrc, bsrc);
           cp_async16(&sg.u[j][w * kPer], usrc + w * kPer);
         } else if (w < 2 * cu) {
-          const T *dsrc = br.delta + (((size_t)b * Lp + l) * 2 + k) * D + d0;
+          const T *dsrc = (l < n_sel ? br.delta + (((size_t)b * n_sel + l) * 2 + k) * D
+                                     : br.delta_tail + (((size_t)b * n_tail + (l - n_sel)) * 2 + k) * D) + d0;
           cp_async16(&sg.dt[j][(w - cu) * kPer], dsrc + (w - cu) * kPer);
         } else {
           const T *usrc, *bsrc;
@@ -453,7 +454,8 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     const actk_branch_args &s = a->br[i < a->n_branches ? i : 0];
     BranchDev<T> &d = P.br[i];
     d.xz = (const T *)s.xz; d.tail = (const T *)s.tail; d.xdbl = (const T *)s.xdbl;
-    d.xdbl_tail = (const T *)s.xdbl_tail; d.delta = (const T *)s.delta; d.idx = s.idx;
+    d.xdbl_tail = (const T *)s.xdbl_tail; d.delta = (const T *)s.delta; d.delta_tail = (const T *)s.delta_tail;
+    d.idx = s.idx;
     d.A = s.A; d.Dskip = s.Dskip; d.dt_bias = s.dt_bias; d.ydir = (T *)s.ydir;
     d.n_sel = s.n_sel; d.n_tail = s.n_tail;
     d.idx_iota = s.n_sel == a->L;   // ascending distinct rows in [0, L): all L of them means idx[p] == p
@@ -462,7 +464,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
       int rc;
       if ((rc = make_map(&M.m[i].xz, dt, es, s.xz, a->D, a->L, a->Bp, kCh))) return rc;
       if ((rc = make_map(&M.m[i].xdbl, dt, es, s.xdbl, a->xw, a->L, a->Bp, 2 * kN))) return rc;
-      if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, Lp, a->Bp, kCh))) return rc;
+      if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, (uint64_t)s.n_sel, a->Bp, kCh))) return rc;
       if ((rc = make_map(&M.m[i].ydir, dt, es, s.ydir, a->D, a->L, 2ull * a->Bp, kCh))) return rc;
     }
   }
@@ -552,10 +554,10 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
       ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: branch %d a_kind=%d", i, s.a_kind);
     if (s.n_sel == 0) continue;
     if (!s.xz || !s.xdbl || !s.delta || !s.idx || !s.A || !s.Dskip || !s.dt_bias || !s.ydir ||
-        (s.n_tail > 0 && (!s.tail || !s.xdbl_tail)))
+        (s.n_tail > 0 && (!s.tail || !s.xdbl_tail || !s.delta_tail)))
       ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: branch %d has a NULL pointer", i);
     if (misaligned(s.xz) || misaligned(s.tail) || misaligned(s.xdbl) || misaligned(s.xdbl_tail) ||
-        misaligned(s.delta) || misaligned(s.ydir))
+        misaligned(s.delta) || misaligned(s.delta_tail) || misaligned(s.ydir))
       ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "masked_scan: branch %d has a pointer not aligned to 16 bytes", i);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

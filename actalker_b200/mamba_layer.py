@@ -229,25 +229,28 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         xw = dv["xw"]
         w_x = dv["w_xproj"].to(xz.dtype)
         xdbl = F.linear(xz, w_x)                                           # (Bp, L, xw)
-        dtr = xdbl[..., 4 * _N:]
-        if n_sel != L:
-            dtr = dtr.index_select(1, idx64s[i] if idx64s is not None else idxs[i].long())
-        xdbl_tail = None
-        if n_tail:
-            xdbl_tail = F.linear(tail, w_x)                                # (Bp, n_tail, xw)
-            dtr = torch.cat([dtr, xdbl_tail[..., 4 * _N:]], dim=1)
+        xdbl_tail = F.linear(tail, w_x) if n_tail else None                # (Bp, n_tail, xw)
         w_dt, A, Dsk, dtb = dv["w_dt"].to(xz.dtype), dv["A"], dv["Ds"], dv["dt_bias"]
         if sliced:   # columns / rows [k*D + lo, k*D + hi) of both directions
             cols = torch.cat([torch.arange(k * D + lo, k * D + hi, device=xz.device) for k in range(2)])
             w_dt, A, Dsk, dtb = w_dt[:, cols].contiguous(), A[cols].contiguous(), Dsk[cols].contiguous(), dtb[cols].contiguous()
             tail = None if tail is None else tail[..., lo:hi].contiguous()
-        delta = torch.matmul(dtr, w_dt)                                    # (Bp, Lp, 2*Dk), sequence order
+        # dt_proj as one GEMM over both directions (block-diagonal weight).  The dt columns of x_dbl are read in
+        # place as a strided 2-D operand (lda = xw): no copy of the (Bp*L, 2R) slice, and the tail rows get their own
+        # small GEMM instead of a concatenation.  Rows are in sequence order: row p <-> latent token idx[p].
+        if n_sel == L:
+            dtr2d = xdbl.view(Bp * L, xw)[:, 4 * _N:]
+        else:
+            dtr2d = xdbl[..., 4 * _N:].index_select(1, idx64s[i] if idx64s is not None else idxs[i].long()).reshape(Bp * n_sel, -1)
+        delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)
+        delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
         if args.xw not in (0, xw):
             raise RuntimeError("branches disagree on the x_proj width")
         args.xw = xw
         b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz_k), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
+        b.delta_tail = _ptr(delta_tail)
         b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(A), _ptr(Dsk), _ptr(dtb), _ptr(ydir)
-        keep += [xdbl, xdbl_tail, delta, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
+        keep += [xdbl, xdbl_tail, delta, delta_tail, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
     live = [i for i, n in enumerate(n_sels) if n > 0]
     if live:
         min_tiles = min(-(-(n_sels[i] + (0 if tails[i] is None else tails[i].shape[1])) // 16) for i in live)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 4
+#define ACTK_ABI_VERSION 5
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -95,9 +95,10 @@ int actk_selective_scan_fwd(const actk_scan_args *args, void *stream);
  *   xdbl      : (Bp, L, xw)       x_proj output of the latent tokens; columns [0, 4*N) hold
  *                                 [B_dir0 | C_dir0 | B_dir1 | C_dir1]; xw*elsize % 16 == 0
  *   xdbl_tail : (Bp, n_tail, xw)  same for the tail tokens
- *   delta     : (Bp, Lp, 2*D)     dt_proj output in SEQUENCE order, Lp = n_sel + n_tail;
+ *   delta     : (Bp, n_sel, 2*D)  dt_proj output of the selected tokens in SEQUENCE order (row p <-> token idx[p]);
  *                                 columns [k*D, (k+1)*D) belong to direction k; position p holds the
  *                                 token at position p for BOTH directions (direction 1 walks p downwards)
+ *   delta_tail: (Bp, n_tail, 2*D) same for the tail tokens (sequence positions n_sel ...)
  *   idx       : (n_sel) int32     ascending latent-token rows selected by the region mask
  *   A         : (2*D, N) fp32     -exp(A_logs);  Dskip, dt_bias: (2*D) fp32
  *   ydir      : (2, Bp, L, D)     per-direction scan output scattered to latent rows idx[p];
@@ -107,7 +108,7 @@ int actk_selective_scan_fwd(const actk_scan_args *args, void *stream);
  *   A branch with n_sel == 0 is skipped (nothing is selected, nothing is written).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
-  const void *xz, *tail, *xdbl, *xdbl_tail, *delta;
+  const void *xz, *tail, *xdbl, *xdbl_tail, *delta, *delta_tail;
   const int *idx;
   const float *A, *Dskip, *dt_bias;
   void *ydir;
