@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
@@ -50,7 +50,8 @@ class MaskedScanArgs(C.Structure):
 class MergeLnArgs(C.Structure):
     _fields_ = [("xz", _vp * 2), ("ydir", _vp * 2), ("selected", _vp * 2),
                 ("gamma", _vp), ("beta", _vp), ("out", _vp), ("eps", _f),
-                ("n_branches", _i), ("Bp", _i), ("L", _i), ("D", _i), ("dtype", _i), ("layernorm", _i)]
+                ("n_branches", _i), ("Bp", _i), ("L", _i), ("D", _i), ("dtype", _i), ("layernorm", _i),
+                ("row_weight", _vp * 2)]
 
 
 class LibraryMissing(RuntimeError):

@@ -69,6 +69,11 @@ __global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ M
           load8(y0 + dir1, g);
 #pragma unroll
           for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(f[e] + g[e]);
+          if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
+            const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
+          }
         } else {
           load8((const T *)a.xz[br] + off + 8 * v, t);
         }

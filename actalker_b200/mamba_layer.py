@@ -30,7 +30,7 @@ from . import _lib
 from .mask import MaskIndex, MaskIndexCache
 from .selective_scan_interface import _DTYPES, _ptr, _stream, a_kind_of
 
-__all__ = ["SS2D_Unit", "SS2D_cond_v10", "MAMBA_AVAILABLE"]
+__all__ = ["SS2D_Unit", "SS2D_cond_v10", "SS2D_cond_v10_wo_id", "SS2D_cond_v8", "SS2D_cond_v9", "MAMBA_AVAILABLE"]
 
 try:
     _lib.load()
@@ -304,7 +304,8 @@ class SS2D_cond_v10(nn.Module):
             raise NotImplementedError("only scan_type='sweep' is live in the reference")
         self.mask_cache = MaskIndexCache()
 
-    def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None):
+    def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None, weights=None,
+                  layernorm=None):
         """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
         ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
         ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
@@ -319,7 +320,10 @@ class SS2D_cond_v10(nn.Module):
         for i, ((yd, xz_k), m) in enumerate(zip(res, (m1, m2))):
             a.xz[i], a.ydir[i], a.selected[i] = xz_k.data_ptr(), yd.data_ptr(), m.selected.data_ptr()
         a.out = _ptr(out)
-        a.layernorm = 1 if ch_slice is None else 0
+        a.layernorm = (1 if ch_slice is None else 0) if layernorm is None else int(layernorm)
+        if weights is not None:                      # v8 / v9: multiplicative blend with the downsampled masks
+            wts = [w.to(xz1.dtype).contiguous() for w in weights]
+            a.row_weight[0], a.row_weight[1] = wts[0].data_ptr(), wts[1].data_ptr()
         if a.layernorm:
             gamma, beta = self.out_norm.weight.to(xz1.dtype), self.out_norm.bias.to(xz1.dtype)
             a.gamma, a.beta = _ptr(gamma), _ptr(beta)
@@ -328,25 +332,82 @@ class SS2D_cond_v10(nn.Module):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
         return out
 
+    use_id = True   # SS2D_cond_v10_wo_id drops the identity token (and has no id_proj)
+
     def project_inputs(self, x, id_emb, conds, masks):
         """The dense front half of forward (mamba_layer.py:1958-1961, 1966, 1972, 1977): in_proj of both
         branches, id / condition projections, cached mask indices."""
         L = x.shape[1]
         audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
-        id_tok = self.act2(self.id_proj(id_emb))
         xz1 = self.in_proj1(x)
         xz2 = self.in_proj2(x)
         m1 = self.mask_cache.get(masks[0], L)
         m2 = self.mask_cache.get(masks[1], L)
-        tail1 = torch.cat([id_tok, self.act1(self.audio_proj(audio_cond))], dim=1)
-        tail2 = torch.cat([id_tok, self.act2(self.exp_proj(exp_cond))], dim=1)
+        tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
+        if self.use_id:
+            id_tok = self.act2(self.id_proj(id_emb))
+            tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
         return xz1.contiguous(), xz2.contiguous(), tail1.contiguous(), tail2.contiguous(), m1, m2
+
+    def _check_forward_only(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(f"actalker_b200.{type(self).__name__} is forward-only (the reference's "
+                                      "inference path, pipeline ...two_ip.py:351); call it under torch.no_grad()")
 
     def forward(self, x, id_emb, conds, masks):
         # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
         # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("actalker_b200.SS2D_cond_v10 is forward-only (the reference's inference path, "
-                                      "pipeline ...two_ip.py:351); call it under torch.no_grad()")
+        self._check_forward_only(x)
         y = self.scan_core(*self.project_inputs(x, id_emb, conds, masks))
         return self.out_proj(y)
+
+
+class SS2D_cond_v10_wo_id(SS2D_cond_v10):
+    """mamba_layer.py:1988-2070: v10 without the identity token (no `id_proj` parameter; `id_emb` is ignored)."""
+    use_id = False
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        del self.id_proj
+
+
+def _full_index(m: MaskIndex, device) -> MaskIndex:
+    """Index of ALL L tokens: v8 / v9 scan every token and blend afterwards."""
+    iota = torch.arange(m.L, device=device)
+    return MaskIndex(idx=iota.to(torch.int32), idx64=iota, selected=torch.ones(m.L, dtype=torch.uint8, device=device),
+                     n_sel=m.L, L=m.L, weight=m.weight)
+
+
+class SS2D_cond_v8(SS2D_cond_v10):
+    """mamba_layer.py:1706-1800, the older multiplicative blend: both branches scan every latent token (plus the id
+    and condition tail), each result is multiplied by its bicubically downsampled mask (:1777-1797), the two are
+    added, then out_norm / out_proj.  Same parameters as v10; same kernels with per-row weights in the merge."""
+
+    def _blend(self, x, id_emb, conds, masks, layernorm):
+        self._check_forward_only(x)
+        xz1, xz2, tail1, tail2, m1, m2 = self.project_inputs(x, id_emb, conds, masks)
+        f1, f2 = _full_index(m1, x.device), _full_index(m2, x.device)
+        return self.scan_core(xz1, xz2, tail1, tail2, f1, f2, weights=[m1.weight, m2.weight], layernorm=layernorm)
+
+    def forward(self, x, id_emb, conds, masks):
+        return self.out_proj(self._blend(x, id_emb, conds, masks, layernorm=True))
+
+
+class SS2D_cond_v9(SS2D_cond_v8):
+    """mamba_layer.py:1802-1899: v8 plus a third bidirectional unit (`fuse_unit`) over the blended sum before
+    out_norm (:1893-1896)."""
+
+    def __init__(self, d_model, d_cond, cond_size=0, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001,
+                 dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True,
+                 bias=False, device=None, dtype=None, size=8, scan_type="scan", num_direction=8, **kwargs):
+        super().__init__(d_model, d_cond, cond_size, d_state, d_conv, expand, dt_rank, dt_min, dt_max, dt_init,
+                         dt_scale, dt_init_floor, dropout, conv_bias, bias, device, dtype, size, scan_type,
+                         num_direction, **kwargs)
+        self.fuse_unit = SS2D_Unit(d_model, d_cond, cond_size, d_state, d_conv, expand, dt_rank, dt_min, dt_max,
+                                   dt_init, dt_scale, dt_init_floor, dropout, conv_bias, bias, device, dtype, size,
+                                   scan_type, num_direction)
+
+    def forward(self, x, id_emb, conds, masks):
+        y = self._blend(x, id_emb, conds, masks, layernorm=False)           # (B', L, D) blended sum
+        y = self.fuse_unit(y.permute(0, 2, 1)).permute(0, 2, 1)
+        return self.out_proj(self.out_norm(y))

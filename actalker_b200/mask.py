@@ -57,6 +57,7 @@ class MaskIndex:
     n_sel: int               # host copy (one sync when the entry is created)
     L: int
     mask_ref: torch.Tensor = None   # keeps the keyed storage alive so its address cannot be recycled
+    weight: torch.Tensor = None     # (L,) downsampled mask values in the mask's dtype (v8/v9 multiplicative blend)
 
     @property
     def full(self) -> bool:
@@ -77,7 +78,8 @@ class MaskIndexCache:
         if hit is not None:
             return hit
         self.misses += 1
-        idx64 = mask_to_index(mask, L)
+        down = downsample(mask[:, 0, :, :], mask.shape[0], L, 1)     # (b, L, 1), the reference's own expression
+        idx64 = down.view(-1).int().nonzero().view(-1)
         if idx64.numel() and int(idx64[-1]) >= L:
             # masks with batch > 1 flatten to b*L entries upstream and then index out of range (:1963);
             # the live pipeline always passes batch 1 (pipeline ...two_ip.py:632-633).
@@ -85,7 +87,7 @@ class MaskIndexCache:
         sel = torch.zeros(L, dtype=torch.uint8, device=mask.device)
         sel[idx64] = 1
         entry = MaskIndex(idx=idx64.to(torch.int32), idx64=idx64, selected=sel, n_sel=int(idx64.numel()), L=L,
-                          mask_ref=mask)
+                          mask_ref=mask, weight=down[0, :, 0].contiguous())
         if len(self._entries) >= self._max:
             self._entries.pop(next(iter(self._entries)))
         self._entries[key] = entry

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 5
+#define ACTK_ABI_VERSION 6
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -162,6 +162,9 @@ typedef struct {
   int dtype;
   int layernorm; /* 1: as above.  0: out[r] = round(t_1 + t_0) only (gamma/beta unused) — the channel-sharded
                     multi-GPU path, where LayerNorm can only run after the all-gather of the channel slices */
+  const void *row_weight[2]; /* NULL, or (L) `dtype`: t_i = round(t_i * row_weight_i[r]) for selected rows — the
+                    multiplicative region blend of the older SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797), whose
+                    weight is the bicubically downsampled mask itself */
 } actk_merge_ln_args;
 
 int actk_merge_layernorm_fwd(const actk_merge_ln_args *args, void *stream);

@@ -32,7 +32,8 @@ def load_golden(name):
     dtype = _DT[str(z["dtype"])] if "dtype" in z.files else torch.float32
     out = {"dtype": dtype, "meta": [int(v) for v in z["meta"]], "sd": {}}
     for k in z.files:
-        if k in ("meta", "dtype"):
+        if k in ("meta", "dtype", "cls"):
+            out["cls"] = str(z["cls"]) if "cls" in z.files else "SS2D_cond_v10"
             continue
         t = torch.from_numpy(z[k])
         if k.startswith("sd."):
@@ -47,6 +48,7 @@ def load_golden(name):
 
 
 LAYER_CASES = ["layer_ones_f32", "layer_rect_f32", "layer_zero_soft_f32", "layer_ones_bf16", "layer_rect_f16"]
+VARIANT_CASES = ["v10woid_rect_f32", "v8_soft_f32", "v8_soft_bf16", "v9_soft_f32"]   # SS2D_cond_v10_wo_id / v8 / v9
 
 
 @pytest.fixture(autouse=True)

@@ -63,14 +63,14 @@ def rect_mask(hw, r0, r1, c0, c1, soft=False):
 
 
 def make_layer_case(ref, name, d_model, d_cond, side, batch, masks, dtype=torch.float32, trained_like=False,
-                    seed_off=0):
+                    seed_off=0, cls="SS2D_cond_v10"):
     torch.manual_seed(SEED + seed_off)
     L = side * side
-    layer = ref.SS2D_cond_v10(d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16,
+    layer = getattr(ref, cls)(d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16,
                               size=side, scan_type="sweep", num_direction=2).eval()
     if trained_like:
         with torch.no_grad():
-            for unit in (layer.audio_unit, layer.exp_unit):
+            for unit in [m for n, m in layer.named_children() if n.endswith("_unit")]:
                 unit.A_logs.add_(0.5 * torch.randn_like(unit.A_logs))
                 unit.Ds.copy_(1.0 + 0.2 * torch.randn_like(unit.Ds))
     if dtype != torch.float32:
@@ -87,7 +87,7 @@ def make_layer_case(ref, name, d_model, d_cond, side, batch, masks, dtype=torch.
         idx = [ref.IPAdapterMaskProcessor.downsample(m[:, 0], m.shape[0], L, 1).view(-1).int().nonzero().view(-1)
                for m in masks]
     out = {"meta": np.array([d_model, d_cond, side, batch], dtype=np.int64),
-           "dtype": np.array(str(dtype).replace("torch.", "")),
+           "dtype": np.array(str(dtype).replace("torch.", "")), "cls": np.array(cls),
            "x": x.float().numpy(), "id_emb": id_emb.float().numpy(), "conds": conds.float().numpy(),
            "mask0": masks[0].float().numpy(), "mask1": masks[1].float().numpy(),
            "idx0": idx[0].numpy(), "idx1": idx[1].numpy(), "y": y.float().numpy()}
@@ -125,6 +125,13 @@ def main():
     make_layer_case(ref, "layer_rect_f16", 32, 64, 8, 2, [rect_mask(64, 32, 56, 16, 48), ones],
                     dtype=torch.float16, trained_like=True, seed_off=5)
     make_unit_case(ref, "unit_f32", 24, 77, 2, seed_off=6)
+    # the older / ablation variants that run on the same kernels
+    soft = rect_mask(64, 8, 56, 8, 56, soft=True)
+    hard = rect_mask(64, 32, 56, 16, 48)
+    make_layer_case(ref, "v10woid_rect_f32", 32, 64, 8, 2, [hard, ones], trained_like=True, seed_off=7, cls="SS2D_cond_v10_wo_id")
+    make_layer_case(ref, "v8_soft_f32", 32, 64, 8, 2, [soft, hard], trained_like=True, seed_off=8, cls="SS2D_cond_v8")
+    make_layer_case(ref, "v8_soft_bf16", 32, 64, 8, 2, [soft, ones], dtype=torch.bfloat16, seed_off=9, cls="SS2D_cond_v8")
+    make_layer_case(ref, "v9_soft_f32", 32, 64, 8, 2, [soft, hard], trained_like=True, seed_off=10, cls="SS2D_cond_v9")
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import LAYER_CASES, load_golden
+from conftest import LAYER_CASES, VARIANT_CASES, load_golden
 from oracle import SS2D_Unit_ref, SS2D_cond_v10_ref, mask_to_index as oracle_mask_to_index, selective_scan_ref
 
 pytestmark = pytest.mark.gpu
@@ -170,11 +170,11 @@ def test_mask_index_bit_exact(dtype):
 
 # ------------------------------------------------------------------------------------------ module seam
 def build_pair(g, device="cuda"):
-    from actalker_b200 import SS2D_cond_v10
+    import actalker_b200
     d_model, d_cond, side, _ = g["meta"]
     kw = dict(d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16, size=side,
               scan_type="sweep", num_direction=2)
-    ours = SS2D_cond_v10(**kw).eval()
+    ours = getattr(actalker_b200, g.get("cls", "SS2D_cond_v10"))(**kw).eval()
     if g["dtype"] != torch.float32:
         ours = ours.to(g["dtype"])
     ours.load_state_dict(g["sd"], strict=True)       # same keys / shapes as the reference (Appendix C)
@@ -185,7 +185,7 @@ def build_pair(g, device="cuda"):
     return ours
 
 
-@pytest.mark.parametrize("case", LAYER_CASES)
+@pytest.mark.parametrize("case", LAYER_CASES + VARIANT_CASES)
 def test_layer_matches_reference_golden(case):
     g = load_golden(case)
     layer = build_pair(g)

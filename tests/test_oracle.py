@@ -189,3 +189,22 @@ def test_layer_direction_symmetry():
     b.load_state_dict(sd)
     with torch.no_grad():
         assert torch.allclose(b(g["x"].flip(-1)), a(g["x"]).flip(-1), rtol=1e-5, atol=1e-6)
+
+
+def test_product_modules_have_the_reference_state_dict_layout():
+    """Drop-in check that needs no GPU: every product module is constructed with the reference's arguments and must
+    expose exactly the parameter names / shapes the real reference classes had when the goldens were made
+    (SURVEY.md Appendix C), so `load_state_dict(strict=True)` of shipped checkpoints keeps working."""
+    import actalker_b200
+    from conftest import VARIANT_CASES
+    for case in LAYER_CASES + VARIANT_CASES:
+        g = load_golden(case)
+        d_model, d_cond, side, _ = g["meta"]
+        layer = getattr(actalker_b200, g.get("cls", "SS2D_cond_v10"))(
+            d_model=d_model, d_cond=d_cond, cond_size=32, dropout=0.1, d_state=16, size=side, scan_type="sweep",
+            num_direction=2)
+        sd = layer.state_dict()
+        assert set(sd) == set(g["sd"]), (case, set(sd) ^ set(g["sd"]))
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(g["sd"][k].shape), (case, k)
+        layer.load_state_dict({k: v.float() for k, v in g["sd"].items()}, strict=True)
