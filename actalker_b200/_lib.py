@@ -72,6 +72,11 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
+    if not os.path.exists(path) and "ACTK_LIB_PATH" not in os.environ:
+        try:                      # fresh checkout: compile in-tree once (nvcc, sm_100a); still no non-CUDA path
+            _build.build()
+        except Exception as e:    # noqa: BLE001 - reported below
+            raise LibraryMissing(f"{path} is missing and building it failed: {e}") from e
     if not os.path.exists(path):
         raise LibraryMissing(
             f"{path} not found: run `python -m actalker_b200.build` (nvcc, sm_100a). "
