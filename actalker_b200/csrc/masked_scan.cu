@@ -20,6 +20,13 @@
 //     pieces with cp.async (LDGSTS) arriving on the same mbarrier, and store y rows with 128-bit STG.
 // One __syncthreads per tile publishes the fp32-widened B|C rows and releases the oldest stage for refill; there
 // is no producer warp and nothing spins.
+//
+// Three launch shapes share the kernel body (template MODE):
+//   plain      (nseg <= 1, chain_chunks <= 1)  grid (D/64, B', 2*branches), one CTA per sequence;
+//   chain      (chain_chunks > 1, the default for launches that fill the GPU)  every sequence is cut into
+//              sequentially dependent chunks drawn from an atomic work counter — balances the 3-vs-4-warp schedulers
+//              and the last wave; bit-identical results;
+//   two-level  (nseg > 1, small batches / one long sequence)  chunk summaries (MODE 1) + scan_carry_kernel + rescan.
 #include <cuda.h>
 #include <string.h>
 

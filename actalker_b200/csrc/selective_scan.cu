@@ -6,7 +6,8 @@
 // Same per-channel register recurrence as the fused layer kernel (scan_core.cuh).  Because the contract is
 // channels-first with arbitrary seqlen (L' = 5217 is odd, so rows are not 16-byte aligned and bulk/TMA copies
 // are not legal), tiles of 64 channels x 32 steps are transposed through padded shared memory with coalesced
-// 64-byte row segments on the global side.  dstate == 16 takes this kernel; other dstate <= 64 a plain one.
+// 64-byte row segments on the global side; the loads of tile i+1 are staged in registers while tile i is scanned.
+// dstate == 16 takes this kernel; other dstate <= 64 a plain one.
 #include "scan_core.cuh"
 
 namespace actk {
