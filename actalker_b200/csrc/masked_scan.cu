@@ -299,7 +299,18 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       const float *bcs = k16 ? &bcf[tr & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
       T *ys = &ybuf[tr & 1][0][tid];
       if (MODE == 1) {
-        for (int r = 0; r < g.nrows; ++r) {
+        int r = 0;
+        if (g.nrows == kT) {
+#pragma unroll 1
+          for (; r < kT; r += kGroup) {
+            const int j0 = k ? kT - 1 - r : r, dj = k ? -1 : 1;
+            sumdt += cs.template run_state<kGroup, true>(
+                [&](int i) { return IO<T>::ld(us + (j0 + dj * i) * kCh); },
+                [&](int i) { return IO<T>::ld(ds + (j0 + dj * i) * kCh); },
+                [&](int i) { return bcs + (j0 + dj * i) * 2 * kN; });
+          }
+        }
+        for (; r < g.nrows; ++r) {
           const int j = k ? kT - 1 - r : r;
           const StepIn si = cs.template prologue<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh));
           uint64_t p[kN / 2];

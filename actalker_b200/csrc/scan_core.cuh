@@ -24,8 +24,8 @@
 namespace actk {
 
 #ifndef ACTK_POLY_PAIRS
-#define ACTK_POLY_PAIRS 1   // state pairs per step whose exp runs on the FMA pipe (general-A path); tuned on B200:
-                            // 0 -> 1.85 ms, 1 -> 1.80 ms, 2 -> 1.95 ms, 3 -> 2.12 ms at config 2
+#define ACTK_POLY_PAIRS 1   // state pairs per step whose exp runs on the FMA pipe (general-A path); tuned on B200 at
+                            // config 2 with chain mode: 0 -> 1.53 ms, 1 -> 1.50 ms, 2 -> 1.59 ms, 3 -> 1.73 ms
 #endif
 constexpr int kPolyPairs = ACTK_POLY_PAIRS;
 
@@ -124,6 +124,23 @@ struct ChannelScan {
       h[2 * q] = fma2(p[2 * q], h[2 * q], mul2(x2, Bq.x));
       h[2 * q + 1] = fma2(p[2 * q + 1], h[2 * q + 1], mul2(x2, Bq.y));
     }
+  }
+
+  // Pipelined state-only run (chunk-summary pass): returns the sum of dt over the NSTEP steps.
+  template <int NSTEP, bool SOFTPLUS, typename LdU, typename LdD, typename Bc>
+  __device__ __forceinline__ float run_state(LdU ld_u, LdD ld_d, Bc bc) {
+    StepIn s[NSTEP];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NSTEP; ++i) { s[i] = prologue<SOFTPLUS>(ld_u(i), ld_d(i)); sum += s[i].dt; }
+    uint64_t p[2][kN / 2];
+    decay(s[0].dt, p[0]);
+#pragma unroll
+    for (int i = 0; i < NSTEP; ++i) {
+      if (i + 1 < NSTEP) decay(s[i + 1].dt, p[(i + 1) & 1]);
+      apply_state(p[i & 1], s[i], bc(i));
+    }
+    return sum;
   }
 
   // Unpipelined convenience form (operator-contract kernel, ragged tails).
