@@ -15,10 +15,11 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
-           "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
+           "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
+           "actk_pack_dt_proj_weight", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
            "actk_scan_algorithmic_bytes"]
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -38,13 +39,14 @@ class ScanArgs(C.Structure):
 class BranchArgs(C.Structure):
     _fields_ = [("xz", _vp), ("tail", _vp), ("xdbl", _vp), ("xdbl_tail", _vp), ("delta", _vp),
                 ("delta_tail", _vp), ("idx", _vp), ("A", _vp), ("Dskip", _vp), ("dt_bias", _vp), ("ydir", _vp),
-                ("n_sel", _i), ("n_tail", _i), ("a_kind", _i)]
+                ("n_sel", _i), ("n_tail", _i), ("a_kind", _i), ("w_dt", _vp)]
 
 
 class MaskedScanArgs(C.Structure):
     _fields_ = [("br", BranchArgs * 2), ("n_branches", _i),
                 ("Bp", _i), ("L", _i), ("D", _i), ("N", _i), ("xw", _i), ("dtype", _i),
-                ("nseg", _i), ("workspace", _vp), ("workspace_bytes", _ll), ("chain_chunks", _i)]
+                ("nseg", _i), ("workspace", _vp), ("workspace_bytes", _ll), ("chain_chunks", _i),
+                ("dt_rank_pad", _i)]
 
 
 class MergeLnArgs(C.Structure):
@@ -92,13 +94,18 @@ def load():
     lib.actk_masked_scan_fwd.argtypes = [C.POINTER(MaskedScanArgs), _vp]
     lib.actk_masked_scan_workspace_bytes.argtypes = [C.POINTER(MaskedScanArgs)]
     lib.actk_masked_scan_workspace_bytes.restype = _ll
+    lib.actk_dt_proj_image_bytes.argtypes = [_i, _i, _i]
+    lib.actk_dt_proj_image_bytes.restype = _ll
+    lib.actk_pack_dt_proj_weight.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
+    lib.actk_pack_dt_proj_weight.restype = _i
     lib.actk_merge_layernorm_fwd.argtypes = [C.POINTER(MergeLnArgs), _vp]
     lib.actk_a_structure.argtypes = [_vp, _i, _i, _f, _vp, _vp]
     lib.actk_gathered_layernorm_fwd.argtypes = [_vp, _i, _ll, _i, _vp, _vp, _f, _vp, _i, _vp]
     lib.actk_gathered_layernorm_fwd.restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll
-    for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_merge_layernorm_fwd", "actk_a_structure"):
+    for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
+           "actk_pack_dt_proj_weight", "actk_merge_layernorm_fwd", "actk_a_structure"):
         getattr(lib, name).restype = _i
     if lib.actk_abi_version() != ABI_VERSION:
         raise LibraryMissing(f"{path}: ABI version {lib.actk_abi_version()} != {ABI_VERSION}; rebuild")

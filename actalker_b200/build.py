@@ -52,14 +52,17 @@ def build(force: bool = False, verbose: bool = False, out: str = None, defs=()) 
     objs = []
     log = []
     tag = os.path.splitext(os.path.basename(out))[0]
-    for src in SOURCES:
+    procs = []
+    for src in SOURCES:   # one nvcc per translation unit, all at once
         obj = os.path.join(LIB_DIR, (tag + "_" if variant else "") + src.replace(".cu", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)
+    for src, pr in procs:
+        so, se = pr.communicate()
+        log.append(se)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{so}\n{se}")
     cmd = [_nvcc(), "-shared", "-o", out, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

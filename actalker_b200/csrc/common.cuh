@@ -30,6 +30,8 @@ void set_error(const char *fmt, ...);
 // ----------------------------------------------------------------------------- dtype traits
 template <typename T> struct IO;
 template <> struct IO<float> {
+  static constexpr bool is_bf16 = false;
+  static __device__ __forceinline__ float zero() { return 0.f; }
   static __device__ __forceinline__ float ld(const float *p) { return *p; }
   static __device__ __forceinline__ float f(float v) { return v; }
   static __device__ __forceinline__ float rnd(float v) { return v; }
@@ -44,6 +46,8 @@ template <> struct IO<float> {
   }
 };
 template <> struct IO<__half> {
+  static constexpr bool is_bf16 = false;
+  static __device__ __forceinline__ __half zero() { return __float2half_rn(0.f); }
   static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
   static __device__ __forceinline__ float f(__half v) { return __half2float(v); }
   static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
@@ -57,6 +61,8 @@ template <> struct IO<__half> {
   }
 };
 template <> struct IO<__nv_bfloat16> {
+  static constexpr bool is_bf16 = true;
+  static __device__ __forceinline__ __nv_bfloat16 zero() { return __float2bfloat16_rn(0.f); }
   static __device__ __forceinline__ float ld(const __nv_bfloat16 *p) {
     return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t *>(p)) << 16);
   }
@@ -195,6 +201,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const void *tmap, in
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst_smem)),
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst_smem, const void *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 // 3-D tiled TMA store (SASS UTMASTG), tracked by the bulk async-group of the issuing thread.

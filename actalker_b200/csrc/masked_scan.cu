@@ -40,12 +40,16 @@ constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::ru
 #ifndef ACTK_STAGES16
 #define ACTK_STAGES16 4
 #endif
-template <typename T>
-constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : ACTK_STAGES16; }
+#ifndef ACTK_STAGES_FUSED
+#define ACTK_STAGES_FUSED 3
+#endif
+// KS > 0: dt_proj is computed in the kernel (16-bit I/O only) from KS 16-wide slabs of the x_dbl dt columns.
+template <typename T, int KS>
+constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : (KS > 0 ? ACTK_STAGES_FUSED : ACTK_STAGES16); }
 
 template <typename T>
 struct BranchDev {
-  const T *xz, *tail, *xdbl, *xdbl_tail, *delta, *delta_tail;
+  const T *xz, *tail, *xdbl, *xdbl_tail, *delta, *delta_tail, *w_dt;
   const int *idx;
   const float *A, *Dskip, *dt_bias;
   T *ydir;
@@ -70,18 +74,95 @@ struct MaskedParams {
   float *chain_state; // [nq][64][16] state handed from chunk c to chunk c+1
 };
 struct alignas(64) BranchMaps {
-  CUtensorMap xz, xdbl, delta, ydir;
+  CUtensorMap xz, xdbl, delta, ydir, xdbl_dt;
 };
 struct alignas(64) MaskedMaps {
   BranchMaps m[2];
 };
 
-template <typename T>
+// One ring slot.  Unfused (KS == 0): the dt_proj output tile arrives from HBM.  Fused: the tile of dt_proj INPUT
+// columns (16*KS wide, zero-padded rank) arrives instead, already in the tensor cores' K-major core-matrix order
+// [k-chunk of 8][token row][8 elements] (a 4-D tensor map writes that order directly), and the CTA produces the
+// 64 x 16 delta tile itself with tcgen05.mma into tensor memory (see the kernel).
+template <typename T, int KS>
 struct alignas(128) Stage {
+  T u[kT][kCh];
+  T bc[kT][2 * kN];
+  T dtin[2 * KS][kT][8];
+};
+template <typename T>
+struct alignas(128) Stage<T, 0> {
   T u[kT][kCh];
   T dt[kT][kCh];
   T bc[kT][2 * kN];
 };
+
+// ---- tcgen05 / tensor-memory helpers for the fused dt_proj (SASS: UTCHMMA, LDTM) --------------------------------
+// delta[ch][tok] = sum_r W[ch][r] * dtin[tok][r]  as D(128 x 16, fp32 in TMEM) = A(128 x K, smem) * B(16 x K, smem)^T,
+// (rows 64-127 of A are whatever follows the 64 weight rows: their results land in TMEM lanes this CTA never reads)
+// both operands K-major without swizzle: 8-row x 16-byte core matrices, contiguous 128 B each; LBO = byte distance
+// between the two k-chunks of one K=16 instruction, SBO = distance between 8-row groups.
+// The descriptor's low word holds (address >> 4) and LBO, the high word SBO and the version: moving the operand by
+// `bytes` adds bytes >> 4 to the low word.
+__device__ __forceinline__ uint32_t umma_desc_lo(const void *smem, uint32_t lbo_bytes) {
+  return ((smem_u32(smem) & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t sbo_bytes) {
+  return (uint64_t)lo | ((uint64_t)((sbo_bytes >> 4) | (1u << 14)) << 32);   // version 1 (sm_100), no swizzle
+}
+// instruction descriptor: fp32 accumulate, A/B both `fmt` (0 = f16, 1 = bf16), both K-major, M = 128, N = 16
+__device__ __forceinline__ constexpr uint32_t umma_idesc_m128n16(uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+}
+// Both are PREDICATED inside the asm instead of sitting in an `if (tid == 0)`: a thread-dependent branch (or a call)
+// in the tile loop made the compiler move the scan loop's address arithmetic from the uniform datapath into vector
+// registers (+6 instructions per step in an issue-bound loop: 1.58 -> 1.72 ms at config 2).  `issue` is non-zero in
+// exactly one thread of the CTA.
+__device__ __forceinline__ void umma_f16(uint32_t issue, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t issue, uint64_t *bar) {   // arrives when all prior MMAs of the thread are done
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc32(uint32_t *slot_smem) {   // one full warp; 32 columns
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(slot_smem)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc32(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(taddr) : "memory");
+}
+// thread i of the warp reads 4 (or 1) consecutive 32-bit columns of TMEM lane (lane field of taddr) + i.
+// The load is asynchronous: tmem_ld4_issue starts it, tmem_ld4_wait makes the registers valid (and ties them to the
+// wait through in/out operands so no use can be scheduled ahead of it).
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_wait(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r0;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0) :: "memory");
+  return __uint_as_float(r0);
+}
 
 struct TileGeo {
   int nrows;    // valid rows (16 except for the last tile)
@@ -100,13 +181,27 @@ struct TileGeo {
 // scans, and publishes (release).  Chunks of one sequence land on different SMs, so every sequence advances at the
 // average rate and fast SMs simply take more items.  A waiting CTA only ever waits for a CTA that drew a smaller
 // ticket, i.e. one that is already running: no deadlock whatever the hardware's dispatch order.
-template <typename T, bool POWER_A, int MODE>
+template <typename T, bool POWER_A, int MODE, int KS>
 __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P,
                                                           const __grid_constant__ MaskedMaps M) {
-  constexpr int S = ring_stages<T>();
+  constexpr int S = ring_stages<T, KS>();
   constexpr bool k16 = sizeof(T) == 2;
-  __shared__ Stage<T> st[S];
+  constexpr bool kFused = KS > 0;
+  // the single-thread TMA work (tile loads, y stores) runs in warp 1 when warp 0 issues the MMAs: both are serial
+  // instruction chains on the tile's critical path, so they go side by side
+  constexpr int kTmaTid = kFused ? 32 : 0;
+  constexpr int RP = 16 * KS;                     // padded dt rank
+  static_assert(!kFused || k16, "the fused dt_proj uses 16-bit tensor-core operands");
+  __shared__ Stage<T, KS> st[S];
   __shared__ alignas(128) T ybuf[2][kT][kCh];
+  // fused: dt_projs_weight rows of this CTA's channels as the MMA's A operand, [k-chunk][channel][8] — the image
+  // actk_pack_dt_proj_weight prepares, fetched with one bulk copy.  64 rows of slack: the M=128 instruction's unused
+  // rows 64-127 of the last k-chunk read them (results never looked at).
+  constexpr uint32_t kWBytes = 2 * KS * kCh * 16;
+  __shared__ alignas(128) T wsm[kFused ? 2 * KS * kCh * 8 + kCh * 8 : 8];
+  __shared__ alignas(8) uint64_t mma_bar[2];
+  __shared__ alignas(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_slot;
   __shared__ alignas(16) float bcf[k16 ? 2 : 1][k16 ? kT : 1][2 * kN];  // fp32 view of B|C for 16-bit I/O
   __shared__ alignas(8) uint64_t full_bar[S];
 
@@ -146,10 +241,24 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], kCh);
     mbar_fence_init();
     if (P.tma_ok) {
-      tmap_prefetch(&maps.xz); tmap_prefetch(&maps.xdbl); tmap_prefetch(&maps.delta); tmap_prefetch(&maps.ydir);
+      tmap_prefetch(&maps.xz); tmap_prefetch(&maps.xdbl); tmap_prefetch(&maps.ydir);
+      tmap_prefetch(kFused ? &maps.xdbl_dt : &maps.delta);
     }
   }
+  if constexpr (kFused) {
+    if (tid == 0) {
+      mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1); mbar_init(&w_bar, 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(&w_bar, kWBytes);   // only the MMA-issuing thread ever waits for the weights
+      bulk_g2s(wsm, br.w_dt + ((size_t)k * P.nblk + bx) * (kWBytes / sizeof(T)), kWBytes, &w_bar);
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc32(&tmem_slot);     // warp 0 owns the allocation (2 x 16 accumulator columns)
+    tc_fence_before();
+  }
   __syncthreads();
+  uint32_t tmem = 0;
+  if constexpr (kFused) { tc_fence_after(); tmem = tmem_slot; }
 
   auto geo = [&](int t) {
     TileGeo g;
@@ -176,29 +285,36 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       const int row = br.idx_iota ? l : __ldg(br.idx + l);
       const size_t tok = (size_t)b * L + row;
       usrc = br.xz + tok * D + d0;
-      bsrc = br.xdbl + tok * P.xw + k * 2 * kN;
+      bsrc = br.xdbl + tok * P.xw;
     } else {
       const size_t tok = (size_t)b * n_tail + (l - n_sel);
       usrc = br.tail + tok * D + d0;
-      bsrc = br.xdbl_tail + tok * P.xw + k * 2 * kN;
+      bsrc = br.xdbl_tail + tok * P.xw;
     }
   };
 
+  uint32_t fastmask = 0;   // fused: bit (tile - t_begin) & 31 = that tile was written by TMA (no proxy fence needed)
   auto issue_load = [&](int t, const TileGeo &g) {
-    Stage<T> &sg = st[(t - t_begin) % S];
+    Stage<T, KS> &sg = st[(t - t_begin) % S];
     uint64_t *bar = &full_bar[(t - t_begin) % S];
+    if constexpr (kFused) {
+      const uint32_t bit = 1u << ((t - t_begin) & 31);
+      fastmask = g.fast ? (fastmask | bit) : (fastmask & ~bit);
+    }
     if (g.fast) {
-      if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)sizeof(Stage<T>));
-        tma_load_3d(&sg.dt[0][0], &maps.delta, k * D + d0, g.l_first, b, bar);
+      if (tid == kTmaTid) {
+        mbar_expect_tx(bar, (uint32_t)sizeof(Stage<T, KS>));
+        if constexpr (kFused) tma_load_4d(&sg.dtin[0][0][0], &maps.xdbl_dt, 0, g.row0, (4 * kN + k * RP) / 8, b, bar);
+        else tma_load_3d(&sg.dt[0][0], &maps.delta, k * D + d0, g.l_first, b, bar);
         tma_load_3d(&sg.u[0][0], &maps.xz, d0, g.row0, b, bar);
         tma_load_3d(&sg.bc[0][0], &maps.xdbl, k * 2 * kN, g.row0, b, bar);
       }
       mbar_arrive(bar);
     } else {
       constexpr int kPer = 16 / sizeof(T);                 // elements per 16-byte piece
-      const int cu = nch / kPer, cb = 2 * kN / kPer;       // pieces per u / delta row, per B|C row
-      const int per_row = 2 * cu + cb;
+      const int cu = nch / kPer, cb = 2 * kN / kPer;       // pieces per u row, per B|C row
+      const int cd = kFused ? RP / kPer : cu;              // pieces per dt-input row (fused) / delta row
+      const int per_row = cu + cd + cb;
       for (int id = tid; id < g.nrows * per_row; id += kCh) {
         const int jj = id / per_row, w = id - jj * per_row;
         const int l = g.l_lo + jj, j = l - g.l_first;
@@ -206,24 +322,56 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
           const T *usrc, *bsrc;
           src_rows(l, usrc, bsrc);
           cp_async16(&sg.u[j][w * kPer], usrc + w * kPer);
-        } else if (w < 2 * cu) {
-          const T *dsrc = (l < n_sel ? br.delta + (((size_t)b * n_sel + l) * 2 + k) * D
-                                     : br.delta_tail + (((size_t)b * n_tail + (l - n_sel)) * 2 + k) * D) + d0;
-          cp_async16(&sg.dt[j][(w - cu) * kPer], dsrc + (w - cu) * kPer);
+        } else if (w < cu + cd) {
+          if constexpr (kFused) {
+            const T *usrc, *bsrc;
+            src_rows(l, usrc, bsrc);
+            cp_async16(&sg.dtin[w - cu][j][0], bsrc + 4 * kN + k * RP + (w - cu) * kPer);
+          } else {
+            const T *dsrc = (l < n_sel ? br.delta + (((size_t)b * n_sel + l) * 2 + k) * D
+                                       : br.delta_tail + (((size_t)b * n_tail + (l - n_sel)) * 2 + k) * D) + d0;
+            cp_async16(&sg.dt[j][(w - cu) * kPer], dsrc + (w - cu) * kPer);
+          }
         } else {
           const T *usrc, *bsrc;
           src_rows(l, usrc, bsrc);
-          cp_async16(&sg.bc[j][(w - 2 * cu) * kPer], bsrc + (w - 2 * cu) * kPer);
+          cp_async16(&sg.bc[j][(w - cu - cd) * kPer], bsrc + k * 2 * kN + (w - cu - cd) * kPer);
         }
       }
       cp_async_arrive_noinc(bar);
     }
   };
 
+  // Fused dt_proj of tile t on the tensor cores (SASS UTCHMMA): D (128 x 16 tile rows, fp32, TMEM columns
+  // [16*(tr&1), +16)) = W (rows 0-63 = this CTA's channels) * dtin(16 x RP)^T, one M=128 instruction per 16 ranks.
+  // Accumulator row r lives in TMEM lane r, so thread tid later reads its own channel with tcgen05.ld (warp w can
+  // reach lanes 32w .. 32w+31); lanes 64-127 hold the unused rows.  Called by ALL lanes of warp 0 (converged): the
+  // address arithmetic stays on the uniform datapath and one elected lane issues — the MMA warp is on the tile's
+  // critical path (the scan is latency-bound per sequence), so every instruction here counts.
+  // Executed by EVERY thread (no thread-dependent branch, see umma_f16); thread 0 is the one that issues.
+  const uint32_t mma_issuer = tid == 0 ? 1u : 0u;
+  auto issue_mma = [&](int t) {
+    if constexpr (kFused) {
+      const int tr1 = t - t_begin, s1 = tr1 % S;
+      if (tr1 == 0) mbar_wait(&w_bar, 0);        // weights landed (first tile of this CTA only)
+      mbar_wait(&full_bar[s1], (tr1 / S) & 1);   // the tile's dt columns have landed
+      if (!((fastmask >> (tr1 & 31)) & 1)) fence_proxy_async();   // ragged tiles are written by cp.async (generic proxy)
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_m128n16(IO<T>::is_bf16 ? 1u : 0u);
+      const uint32_t d = tmem + (uint32_t)(tr1 & 1) * kT;
+      const uint32_t alo = umma_desc_lo(wsm, kCh * 16), blo = umma_desc_lo(&st[s1].dtin[0][0][0], kT * 16);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        umma_f16(mma_issuer, d, umma_desc(alo + ks * (2 * kCh * 16 >> 4), 128), umma_desc(blo + ks * (2 * kT * 16 >> 4), 128),
+                 idesc, ks > 0);
+      umma_commit(mma_issuer, &mma_bar[tr1 & 1]);
+    }
+  };
+
   T *ydst = br.ydir + ((size_t)k * P.Bp + b) * L * D + d0;
   auto store_y = [&](int t, const TileGeo &g) {
     if (g.fast) {
-      if (tid == 0) {
+      if (tid == kTmaTid) {
         tma_store_3d(&maps.ydir, d0, g.row0, k * P.Bp + b, &ybuf[(t - t_begin) & 1][0][0]);
         bulk_commit();
       }
@@ -273,6 +421,10 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   // ring slots and y double-buffer are indexed by the tile number relative to the chunk start
   for (int t = t_begin; t < min(t_begin + S - 1, t_end); ++t) issue_load(t, geo(t));
 
+  if constexpr (kFused) {
+    if (t_begin < t_end) issue_mma(t_begin);
+  }
+
   TileGeo prev = {};
   for (int t = t_begin; t < t_end; ++t) {
     const int tr = t - t_begin;
@@ -289,30 +441,60 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       dst[0] = lo;
       dst[1] = hi;
     }
-    if (tid == 0) bulk_wait_read<0>();  // the y tile stored two iterations ago has left ybuf[t & 1]
-    __syncthreads();                    // B|C published; everyone is done with tile t-1 (its stage and y tile)
+    if (tid == kTmaTid) bulk_wait_read<0>();  // the y tile stored two iterations ago has left ybuf[t & 1]
+    if constexpr (kFused) tc_fence_before();   // this thread's TMEM reads of tile t-1 precede the barrier
+    __syncthreads();                    // B|C published; everyone is done with tile t-1 (its stage, y tile, TMEM buffer)
     if (MODE != 1 && tr > 0) store_y(t - 1, prev);
     if (t + S - 1 < t_end) issue_load(t + S - 1, geo(t + S - 1));
+    uint32_t tacc = 0;                  // TMEM address of this thread's delta row: lane = channel, column = tile row
+    if constexpr (kFused) {
+      if (t + 1 < t_end) issue_mma(t + 1);                      // tile t+1's delta forms while tile t is scanned
+      mbar_wait(&mma_bar[tr & 1], (tr >> 1) & 1);               // tile t's delta is in TMEM
+      tc_fence_after();
+      tacc = tmem + ((uint32_t)(tid & 32) << 16) + (uint32_t)(tr & 1) * kT;
+    }
 
-    if (live) {
-      const T *us = &st[s].u[0][tid], *ds = &st[s].dt[0][tid];
+    // Fused: tcgen05.ld is warp-collective, so lanes of a partial channel block run along (their u columns are
+    // zero-filled / never stored; their y columns are clipped by the stores).
+    if (live || kFused) {
+      const T *us = &st[s].u[0][tid];
+      const T *ds = nullptr;
+      if constexpr (!kFused) ds = &st[s].dt[0][tid];
       const float *bcs = k16 ? &bcf[tr & 1][0][0] : reinterpret_cast<const float *>(&st[s].bc[0][0]);
       T *ys = &ybuf[tr & 1][0][tid];
+      // raw delta of tile row j for this thread's channel, rounded to T where the reference holds the dts tensor
+      auto delta_row = [&](int j) -> float {
+        if constexpr (kFused) return IO<T>::rnd(tmem_ld1(tacc + j));
+        else return IO<T>::ld(ds + j * kCh);
+      };
       if (MODE == 1) {
         int r = 0;
         if (g.nrows == kT) {
+          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
+          if constexpr (kFused) { tmem_ld4_issue(tacc + (k ? kT - kGroup : 0), dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
           for (; r < kT; r += kGroup) {
             const int j0 = k ? kT - 1 - r : r, dj = k ? -1 : 1;
+            if constexpr (kFused) {   // next group's delta values travel from TMEM while this group is scanned
+              if (r + kGroup < kT) tmem_ld4_issue(tacc + (k ? kT - 2 * kGroup - r : r + kGroup), dn);
+            }
             sumdt += cs.template run_state<kGroup, true>(
                 [&](int i) { return IO<T>::ld(us + (j0 + dj * i) * kCh); },
-                [&](int i) { return IO<T>::ld(ds + (j0 + dj * i) * kCh); },
+                [&](int i) {
+                  if constexpr (kFused) return IO<T>::rnd(__uint_as_float(k ? dv[kGroup - 1 - i] : dv[i]));
+                  else return IO<T>::ld(ds + (j0 + dj * i) * kCh);
+                },
                 [&](int i) { return bcs + (j0 + dj * i) * 2 * kN; });
+            if constexpr (kFused) {
+              tmem_ld4_wait(dn);
+#pragma unroll
+              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+            }
           }
         }
         for (; r < g.nrows; ++r) {
           const int j = k ? kT - 1 - r : r;
-          const StepIn si = cs.template prologue<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh));
+          const StepIn si = cs.template prologue<true>(IO<T>::ld(us + j * kCh), delta_row(j));
           uint64_t p[kN / 2];
           cs.decay(si.dt, p);
           cs.apply_state(p, si, bcs + j * 2 * kN);
@@ -321,33 +503,59 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       } else if (g.nrows == kT) {
         // smem row of step r: r (direction 0) or 15 - r (direction 1); kGroup steps are software-pipelined
         if (k == 0) {
+          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
+          if constexpr (kFused) { tmem_ld4_issue(tacc, dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
           for (int r0 = 0; r0 < kT; r0 += kGroup) {
             const T *u0 = us + r0 * kCh, *dl0 = ds + r0 * kCh;
             const float *b0 = bcs + r0 * 2 * kN;
             T *y0 = ys + r0 * kCh;
+            if constexpr (kFused) {   // next group's delta values travel from TMEM while this group is scanned
+              if (r0 + kGroup < kT) tmem_ld4_issue(tacc + r0 + kGroup, dn);
+            }
             cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 + i * kCh); },
-                                          [&](int i) { return IO<T>::ld(dl0 + i * kCh); },
+                                          [&](int i) {
+                                            if constexpr (kFused) return IO<T>::rnd(__uint_as_float(dv[i]));
+                                            else return IO<T>::ld(dl0 + i * kCh);
+                                          },
                                           [&](int i) { return b0 + i * 2 * kN; },
                                           [&](int i, float y) { IO<T>::st(y0 + i * kCh, y); });
+            if constexpr (kFused) {
+              tmem_ld4_wait(dn);
+#pragma unroll
+              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+            }
           }
         } else {
+          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
+          if constexpr (kFused) { tmem_ld4_issue(tacc + kT - kGroup, dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
           for (int r0 = 0; r0 < kT; r0 += kGroup) {
             const int j0 = kT - 1 - r0;
             const T *u0 = us + j0 * kCh, *dl0 = ds + j0 * kCh;
             const float *b0 = bcs + j0 * 2 * kN;
             T *y0 = ys + j0 * kCh;
+            if constexpr (kFused) {
+              if (r0 + kGroup < kT) tmem_ld4_issue(tacc + kT - 2 * kGroup - r0, dn);
+            }
             cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 - i * kCh); },
-                                          [&](int i) { return IO<T>::ld(dl0 - i * kCh); },
+                                          [&](int i) {
+                                            if constexpr (kFused) return IO<T>::rnd(__uint_as_float(dv[kGroup - 1 - i]));
+                                            else return IO<T>::ld(dl0 - i * kCh);
+                                          },
                                           [&](int i) { return b0 - i * 2 * kN; },
                                           [&](int i, float y) { IO<T>::st(y0 - i * kCh, y); });
+            if constexpr (kFused) {
+              tmem_ld4_wait(dn);
+#pragma unroll
+              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+            }
           }
         }
       } else {
         for (int r = 0; r < g.nrows; ++r) {
           const int j = k ? kT - 1 - r : r;
-          float y = cs.template step<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh), bcs + j * 2 * kN);
+          float y = cs.template step<true>(IO<T>::ld(us + j * kCh), delta_row(j), bcs + j * 2 * kN);
           IO<T>::st(ys + j * kCh, y);
         }
       }
@@ -362,6 +570,11 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       for (int j = 0; j < kN / 2; ++j) upk(cs.h[j], he[2 * j], he[2 * j + 1]);
       P.ws_sumdt[ws_row + tid] = sumdt;
     }
+    if constexpr (kFused) {
+      tc_fence_before();
+      __syncthreads();
+      if (tid < 32) tmem_dealloc32(tmem);
+    }
     return;
   }
   if (MODE == 2 && seg + 1 < nseg) {   // publish the state for the next chunk of this sequence (release)
@@ -375,12 +588,16 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     }
     __threadfence();
   }
-  if (tid == 0) bulk_wait_read<0>();
+  if (tid == kTmaTid) bulk_wait_read<0>();
+  if constexpr (kFused) tc_fence_before();
   __syncthreads();
+  if constexpr (kFused) {
+    if (tid < 32) tmem_dealloc32(tmem);   // every thread's TMEM reads are behind the barrier
+  }
   if (MODE == 2 && seg + 1 < nseg && tid == 0)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.chain_flag + q), "r"(seg + 1) : "memory");
   if (t_end > t_begin) store_y(t_end - 1, prev);
-  if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
+  if (tid == kTmaTid) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
 }
 
 // Inter-chunk carry of the two-level scan: one thread per (batch, branch, direction, channel) walks the nseg
@@ -440,6 +657,50 @@ static int make_map(CUtensorMap *m, CUtensorMapDataType dt, int es, const void *
   return ACTK_OK;
 }
 
+// One kernel launch for a given (T, KS); MODE and POWER_A are runtime here.
+template <typename T, int KS>
+static void launch_ks(bool pw, int mode, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P, const MaskedMaps &M) {
+  if (mode == 2) {
+    if (pw) masked_scan_kernel<T, true, 2, KS><<<grid, kCh, 0, stream>>>(P, M);
+    else masked_scan_kernel<T, false, 2, KS><<<grid, kCh, 0, stream>>>(P, M);
+  } else if (mode == 1) {
+    if (pw) masked_scan_kernel<T, true, 1, KS><<<grid, kCh, 0, stream>>>(P, M);
+    else masked_scan_kernel<T, false, 1, KS><<<grid, kCh, 0, stream>>>(P, M);
+  } else {
+    if (pw) masked_scan_kernel<T, true, 0, KS><<<grid, kCh, 0, stream>>>(P, M);
+    else masked_scan_kernel<T, false, 0, KS><<<grid, kCh, 0, stream>>>(P, M);
+  }
+}
+template <typename T>
+static void launch_any(int ks, bool pw, int mode, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P,
+                       const MaskedMaps &M) {
+  if constexpr (sizeof(T) == 2) {
+    switch (ks) {
+      case 2: return launch_ks<T, 2>(pw, mode, grid, stream, P, M);
+      case 3: return launch_ks<T, 3>(pw, mode, grid, stream, P, M);
+      case 5: return launch_ks<T, 5>(pw, mode, grid, stream, P, M);
+      default: break;
+    }
+  }
+  launch_ks<T, 0>(pw, mode, grid, stream, P, M);
+}
+
+// dt-input columns of x_dbl as (8 elements, rows, 16-byte chunks of a row, outer): a box of (8, kT, rp/8, 1) lands
+// in shared memory as [chunk][row][8] — the K-major core-matrix order tcgen05.mma reads without swizzle.
+static int make_map_dtin(CUtensorMap *m, CUtensorMapDataType dt, int es, const void *base, uint64_t xw, uint64_t rows,
+                         uint64_t outer, uint32_t rp) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
+  cuuint64_t dims[4] = {8, rows, xw / 8, outer};
+  cuuint64_t strides[3] = {xw * es, 16, xw * rows * es};
+  cuuint32_t box[4] = {8, (cuuint32_t)kT, rp / 8, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled (dt columns) failed with CUresult %d", (int)r);
+  return ACTK_OK;
+}
+
 template <typename T>
 static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   MaskedParams<T> P;
@@ -449,7 +710,8 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   const int nseg = a->nseg > 1 ? a->nseg : 1;
   P.nseg = nseg;
   P.ws_hend = P.ws_sumdt = P.ws_h0 = nullptr;
-  P.chain_ctr = P.chain_flag = nullptr; P.chain_state = nullptr; P.nq = P.nblk = 0;
+  P.chain_ctr = P.chain_flag = nullptr; P.chain_state = nullptr; P.nq = 0;
+  P.nblk = (a->D + kCh - 1) / kCh;
   const bool chain = a->chain_chunks > 1;
   if (chain && a->nseg > 1) ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg and chain_chunks are mutually exclusive");
   if (nseg > 1) {
@@ -465,6 +727,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
   // (zero fill on load, clipping on store), so any D >= 64 qualifies (channel-sharded slices such as D/8 = 80)
   P.tma_ok = (a->D >= kCh) ? 1 : 0;
   const int es = sizeof(T);
+  const int ks = a->dt_rank_pad / 16;   // 0: delta tensors given; 2/3/5: dt_proj fused into the scan
   const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                          : (a->dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                  : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
@@ -473,6 +736,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     BranchDev<T> &d = P.br[i];
     d.xz = (const T *)s.xz; d.tail = (const T *)s.tail; d.xdbl = (const T *)s.xdbl;
     d.xdbl_tail = (const T *)s.xdbl_tail; d.delta = (const T *)s.delta; d.delta_tail = (const T *)s.delta_tail;
+    d.w_dt = (const T *)s.w_dt;
     d.idx = s.idx;
     d.A = s.A; d.Dskip = s.Dskip; d.dt_bias = s.dt_bias; d.ydir = (T *)s.ydir;
     d.n_sel = s.n_sel; d.n_tail = s.n_tail;
@@ -482,7 +746,9 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
       int rc;
       if ((rc = make_map(&M.m[i].xz, dt, es, s.xz, a->D, a->L, a->Bp, kCh))) return rc;
       if ((rc = make_map(&M.m[i].xdbl, dt, es, s.xdbl, a->xw, a->L, a->Bp, 2 * kN))) return rc;
-      if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, (uint64_t)s.n_sel, a->Bp, kCh))) return rc;
+      if (ks) {
+        if ((rc = make_map_dtin(&M.m[i].xdbl_dt, dt, es, s.xdbl, a->xw, a->L, a->Bp, 16 * ks))) return rc;
+      } else if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, (uint64_t)s.n_sel, a->Bp, kCh))) return rc;
       if ((rc = make_map(&M.m[i].ydir, dt, es, s.ydir, a->D, a->L, 2ull * a->Bp, kCh))) return rc;
     }
   }
@@ -508,15 +774,13 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
       P.chain_ctr = P.chain_flag + P.nq;
       ACTK_CUDA_OK(cudaMemsetAsync(P.chain_flag, 0, ((size_t)P.nq + 1) * sizeof(int), stream));
       const unsigned nblocks = (unsigned)P.nq * a->chain_chunks;
-      if (pw) masked_scan_kernel<T, true, 2><<<nblocks, kCh, 0, stream>>>(P, M);
-      else masked_scan_kernel<T, false, 2><<<nblocks, kCh, 0, stream>>>(P, M);
+      launch_any<T>(ks, pw, 2, dim3(nblocks), stream, P, M);
       ACTK_CUDA_OK(cudaGetLastError());
       i = j;
       continue;
     }
     if (nseg > 1) {   // level 1: chunk summaries; level 2: carries; then the scan proper starts every chunk from its carry
-      if (pw) masked_scan_kernel<T, true, 1><<<grid, kCh, 0, stream>>>(P, M);
-      else masked_scan_kernel<T, false, 1><<<grid, kCh, 0, stream>>>(P, M);
+      launch_any<T>(ks, pw, 1, grid, stream, P, M);
       ACTK_CUDA_OK(cudaGetLastError());
       const float *A0 = (i == 0) ? a->br[0].A : nullptr;
       const float *A1 = (i <= 1 && j >= 2) ? a->br[1].A : nullptr;
@@ -525,8 +789,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
                                                                           a->D, nseg);
       ACTK_CUDA_OK(cudaGetLastError());
     }
-    if (pw) masked_scan_kernel<T, true, 0><<<grid, kCh, 0, stream>>>(P, M);
-    else masked_scan_kernel<T, false, 0><<<grid, kCh, 0, stream>>>(P, M);
+    launch_any<T>(ks, pw, 0, grid, stream, P, M);
     ACTK_CUDA_OK(cudaGetLastError());
     i = j;
   }
@@ -538,6 +801,51 @@ static bool misaligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) &
 }  // namespace actk
 
 using namespace actk;
+
+namespace actk {
+// dt_projs_weight (2, D, R) -> per (direction, 64-channel block) shared-memory image of the fused dt_proj's A operand:
+// [k-chunk of 8 ranks][channel of the block][8] (the K-major core-matrix order of masked_scan_kernel's issue_mma),
+// rank zero-padded to rp, channels >= D zero.  One thread per 16-byte piece.
+template <typename T>
+__global__ void pack_dt_weight_kernel(const T *__restrict__ w, T *__restrict__ img, int D, int R, int rp, int nblk) {
+  const int pieces = rp / 8;
+  const long long n = 2LL * nblk * pieces * kCh;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = (int)(i % kCh), c = (int)((i / kCh) % pieces), bx = (int)((i / ((long long)kCh * pieces)) % nblk);
+  const int k = (int)(i / ((long long)kCh * pieces * nblk));
+  const int ch = bx * kCh + slot;
+  T *dst = img + i * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int r = c * 8 + e;
+    dst[e] = (ch < D && r < R) ? w[((size_t)k * D + ch) * R + r] : IO<T>::zero();
+  }
+}
+}  // namespace actk
+
+extern "C" long long actk_dt_proj_image_bytes(int D, int dt_rank_pad, int elsize) {
+  return 2LL * ((D + kCh - 1) / kCh) * kCh * dt_rank_pad * elsize;
+}
+
+extern "C" int actk_pack_dt_proj_weight(const void *w, int D, int R, int dt_rank_pad, int dtype, void *img, void *stream) {
+  if (!w || !img) ACTK_FAIL(ACTK_ERR_BAD_ARG, "pack_dt_proj_weight: NULL pointer");
+  if (dtype != ACTK_F16 && dtype != ACTK_BF16) ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "pack_dt_proj_weight: dtype=%d (f16 / bf16)", dtype);
+  if (D <= 0 || R <= 0 || R > dt_rank_pad || (dt_rank_pad != 32 && dt_rank_pad != 48 && dt_rank_pad != 80))
+    ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "pack_dt_proj_weight: D=%d R=%d dt_rank_pad=%d", D, R, dt_rank_pad);
+  if (misaligned(img)) ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "pack_dt_proj_weight: image not aligned to 16 bytes");
+  const int nblk = (D + kCh - 1) / kCh;
+  const long long n = 2LL * nblk * (dt_rank_pad / 8) * kCh;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (dtype == ACTK_F16)
+    pack_dt_weight_kernel<__half><<<blocks, 128, 0, st>>>((const __half *)w, (__half *)img, D, R, dt_rank_pad, nblk);
+  else
+    pack_dt_weight_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>((const __nv_bfloat16 *)w, (__nv_bfloat16 *)img, D, R,
+                                                                   dt_rank_pad, nblk);
+  ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
+}
 
 extern "C" long long actk_masked_scan_workspace_bytes(const actk_masked_scan_args *a) {
   if (!a) return 0;
@@ -561,6 +869,14 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
     ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: chain_chunks=%d (0/1 = off, <= 1024)", a->chain_chunks);
   if (a->nseg < 0 || a->nseg > 4096) ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: nseg=%d (0/1 = single level, <= 4096)", a->nseg);
   const int es = a->dtype == ACTK_F32 ? 4 : 2;
+  const int rp = a->dt_rank_pad;
+  if (rp != 0) {
+    if (es != 2) ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "masked_scan: the fused dt_proj (dt_rank_pad=%d) needs f16 / bf16 I/O", rp);
+    if (rp != 32 && rp != 48 && rp != 80)
+      ACTK_FAIL(ACTK_ERR_UNSUPPORTED, "masked_scan: dt_rank_pad=%d, this build has 32 / 48 / 80 (0 = delta tensors given)", rp);
+    if (a->xw % 8 != 0 || a->xw < 4 * kN + 2 * rp)
+      ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: xw=%d < 4N + 2*dt_rank_pad = %d", a->xw, 4 * kN + 2 * rp);
+  }
   if ((a->D * es) % 16 != 0)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "masked_scan: D=%d must be a multiple of %d (16-byte channel rows)", a->D, 16 / es);
   if ((a->xw * es) % 16 != 0) ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "masked_scan: xdbl row pitch %d B not a multiple of 16", a->xw * es);
@@ -571,11 +887,13 @@ extern "C" int actk_masked_scan_fwd(const actk_masked_scan_args *a, void *stream
     if (s.a_kind != ACTK_A_GENERAL && s.a_kind != ACTK_A_POWER)
       ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: branch %d a_kind=%d", i, s.a_kind);
     if (s.n_sel == 0) continue;
-    if (!s.xz || !s.xdbl || !s.delta || !s.idx || !s.A || !s.Dskip || !s.dt_bias || !s.ydir ||
-        (s.n_tail > 0 && (!s.tail || !s.xdbl_tail || !s.delta_tail)))
+    if (!s.xz || !s.xdbl || !s.idx || !s.A || !s.Dskip || !s.dt_bias || !s.ydir ||
+        (s.n_tail > 0 && (!s.tail || !s.xdbl_tail)) ||
+        (rp == 0 && (!s.delta || (s.n_tail > 0 && !s.delta_tail))) || (rp != 0 && !s.w_dt))
       ACTK_FAIL(ACTK_ERR_BAD_ARG, "masked_scan: branch %d has a NULL pointer", i);
     if (misaligned(s.xz) || misaligned(s.tail) || misaligned(s.xdbl) || misaligned(s.xdbl_tail) ||
-        misaligned(s.delta) || misaligned(s.delta_tail) || misaligned(s.ydir))
+        (rp == 0 && (misaligned(s.delta) || misaligned(s.delta_tail))) || (rp != 0 && misaligned(s.w_dt)) ||
+        misaligned(s.ydir))
       ACTK_FAIL(ACTK_ERR_BAD_ALIGN, "masked_scan: branch %d has a pointer not aligned to 16 bytes", i);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as ct
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -64,6 +65,23 @@ class _timed:
 
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
+
+
+_FUSED_KSLABS = (2, 3, 5)   # 16-wide rank slabs the fused dt_proj kernels are built for (dt_rank_pad 32 / 48 / 80)
+# SURVEY §8 row f1.  True (or ACTK_FUSE_DT=1 in the environment): with 16-bit activations the scan kernel computes
+# dt_proj itself per tile (tcgen05.mma into tensor memory) and no delta tensor exists.  Off by default: measured on
+# B200 at config 2 the per-tile issue / wait instructions cost the issue-bound scan +0.19 ms (1.51 -> 1.70 ms) while
+# the two cuBLAS dt_proj GEMMs they replace cost 0.14 ms.
+FUSE_DT_PROJ = os.environ.get("ACTK_FUSE_DT", "0") == "1"
+
+
+def _rank_pad(R: int):
+    """(padded rank, fusable): the dt_proj input of each direction occupies a block of `padded rank` x_dbl columns.
+    Ranks up to 80 (d_model <= 1280 with dt_rank='auto') round up to a width the in-kernel mma.sync dt_proj handles."""
+    for ks in _FUSED_KSLABS:
+        if R <= 16 * ks:
+            return 16 * ks, True
+    return _pad8(R), False
 
 
 class SS2D_Unit(nn.Module):
@@ -136,21 +154,39 @@ class SS2D_Unit(nn.Module):
             raise NotImplementedError(f"kernels are built for num_direction=2, d_state={_N} (the live layer); "
                                       f"got K={K}, d_state={N}")
         with torch.no_grad():
-            xw = _pad8(2 * K * N + K * R)
+            Rp, fusable = _rank_pad(R)
+            xw = 2 * K * N + K * Rp
             wx = self.x_proj_weight                                   # (K, R+2N, D)
-            w = wx.new_zeros(xw, D)
+            w = wx.new_zeros(xw, D)                                   # rows [B_0|C_0|B_1|C_1 | dt_0 (Rp) | dt_1 (Rp)]
             for k in range(K):
                 w[k * 2 * N:k * 2 * N + 2 * N] = wx[k, R:R + 2 * N]   # [B_k | C_k]
-                w[2 * K * N + k * R:2 * K * N + (k + 1) * R] = wx[k, :R]
-            wbd = wx.new_zeros(xw - 2 * K * N, K * D)                 # block-diagonal dt_proj, (K*R [+pad], K*D)
+                w[2 * K * N + k * Rp:2 * K * N + k * Rp + R] = wx[k, :R]   # rank rows, zero-padded to Rp
+            wbd = wx.new_zeros(K * Rp, K * D)                         # block-diagonal dt_proj for the GEMM route
             for k in range(K):
-                wbd[k * R:(k + 1) * R, k * D:(k + 1) * D] = self.dt_projs_weight[k].t()
+                wbd[k * Rp:k * Rp + R, k * D:(k + 1) * D] = self.dt_projs_weight[k].t()
             A = (-torch.exp(self.A_logs.float())).contiguous()        # (K*D, N), as mamba_layer.py:1530
-            d = {"xw": xw, "w_xproj": w.contiguous(), "w_dt": wbd.contiguous(), "A": A,
+            d = {"xw": xw, "w_xproj": w.contiguous(), "w_dt": wbd.contiguous(),
+                 "rank_pad": Rp, "fusable": fusable, "A": A,
                  "Ds": self.Ds.float().contiguous().view(-1), "dt_bias": self.dt_projs_bias.float().contiguous().view(-1),
                  "a_kind": a_kind_of(A) if A.is_cuda else _lib.ACTK_A_GENERAL}
         self._derived, self._derived_key = d, key
         return d
+
+    def dt_image(self, lo: int, hi: int, dtype) -> torch.Tensor:
+        """Tensor-core operand image of dt_projs_weight[:, lo:hi] for the fused dt_proj (actk_pack_dt_proj_weight),
+        cached with the other derived weights (rebuilt when a parameter changes)."""
+        dv = self.derived()
+        key = ("dt_image", lo, hi, dtype)
+        if key not in dv:
+            lib = _lib.load()
+            w = self.dt_projs_weight.detach()[:, lo:hi].to(dtype).contiguous()          # (K, Dk, R)
+            Dk, R, rp = hi - lo, self.dt_rank, dv["rank_pad"]
+            img = torch.empty(lib.actk_dt_proj_image_bytes(Dk, rp, w.element_size()), dtype=torch.uint8, device=w.device)
+            with torch.cuda.device(w.device):
+                _lib.check(lib.actk_pack_dt_proj_weight(_ptr(w), Dk, R, rp, _DTYPES[dtype], _ptr(img), _stream(w)),
+                           "actk_pack_dt_proj_weight")
+            dv[key] = img
+        return dv[key]
 
     def forward_core(self, x: torch.Tensor):
         """x: (B, D, L) -> (B, D, L).  Same contract as upstream; internally token-major."""
@@ -230,25 +266,34 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         w_x = dv["w_xproj"].to(xz.dtype)
         xdbl = F.linear(xz, w_x)                                           # (Bp, L, xw)
         xdbl_tail = F.linear(tail, w_x) if n_tail else None                # (Bp, n_tail, xw)
-        w_dt, A, Dsk, dtb = dv["w_dt"].to(xz.dtype), dv["A"], dv["Ds"], dv["dt_bias"]
+        A, Dsk, dtb = dv["A"], dv["Ds"], dv["dt_bias"]
+        fused = FUSE_DT_PROJ and dv["fusable"] and xz.element_size() == 2
+        w_dt = unit.dt_image(lo, hi, xz.dtype) if fused else dv["w_dt"].to(xz.dtype)
         if sliced:   # columns / rows [k*D + lo, k*D + hi) of both directions
             cols = torch.cat([torch.arange(k * D + lo, k * D + hi, device=xz.device) for k in range(2)])
-            w_dt, A, Dsk, dtb = w_dt[:, cols].contiguous(), A[cols].contiguous(), Dsk[cols].contiguous(), dtb[cols].contiguous()
+            A, Dsk, dtb = A[cols].contiguous(), Dsk[cols].contiguous(), dtb[cols].contiguous()
+            w_dt = w_dt if fused else w_dt[:, cols].contiguous()
             tail = None if tail is None else tail[..., lo:hi].contiguous()
-        # dt_proj as one GEMM over both directions (block-diagonal weight).  The dt columns of x_dbl are read in
-        # place as a strided 2-D operand (lda = xw): no copy of the (Bp*L, 2R) slice, and the tail rows get their own
-        # small GEMM instead of a concatenation.  Rows are in sequence order: row p <-> latent token idx[p].
-        if n_sel == L:
-            dtr2d = xdbl.view(Bp * L, xw)[:, 4 * _N:]
-        else:
-            dtr2d = xdbl[..., 4 * _N:].index_select(1, idx64s[i] if idx64s is not None else idxs[i].long()).reshape(Bp * n_sel, -1)
-        delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)
-        delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
-        if args.xw not in (0, xw):
-            raise RuntimeError("branches disagree on the x_proj width")
-        args.xw = xw
+        delta = delta_tail = None
+        if not fused:
+            # dt_proj as one GEMM over both directions (block-diagonal weight).  The dt columns of x_dbl are read in
+            # place as a strided 2-D operand (lda = xw): no copy of the (Bp*L, 2Rp) slice, and the tail rows get their
+            # own small GEMM instead of a concatenation.  Rows are in sequence order: row p <-> latent token idx[p].
+            if n_sel == L:
+                dtr2d = xdbl.view(Bp * L, xw)[:, 4 * _N:]
+            else:
+                dtr2d = xdbl[..., 4 * _N:].index_select(1, idx64s[i] if idx64s is not None else idxs[i].long()).reshape(Bp * n_sel, -1)
+            delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)
+            delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
+        # fused: the scan kernel multiplies each 16-token tile of dt columns by w_dt on the tensor cores itself
+        # (mma.sync, fp32 accumulate, one rounding to the activation dtype) — no delta tensor, no dt_proj launch
+        rp = dv["rank_pad"] if fused else 0
+        if args.xw not in (0, xw) or (args.xw != 0 and args.dt_rank_pad != rp):
+            raise RuntimeError("branches disagree on the x_proj width / dt rank")
+        args.xw, args.dt_rank_pad = xw, rp
         b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz_k), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
         b.delta_tail = _ptr(delta_tail)
+        b.w_dt = _ptr(w_dt) if fused else None
         b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(A), _ptr(Dsk), _ptr(dtb), _ptr(ydir)
         keep += [xdbl, xdbl_tail, delta, delta_tail, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
     live = [i for i, n in enumerate(n_sels) if n > 0]

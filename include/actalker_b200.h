@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 6
+#define ACTK_ABI_VERSION 7
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -114,6 +114,9 @@ typedef struct {
   void *ydir;
   int n_sel, n_tail;
   int a_kind; /* actk_a_kind */
+  const void *w_dt; /* fused dt_proj (dt_rank_pad != 0): the image actk_pack_dt_proj_weight makes of
+                       dt_projs_weight (mamba_layer.py:1443) for THIS D (a channel slice packs its own rows);
+                       delta / delta_tail are then unused */
 } actk_branch_args;
 
 typedef struct {
@@ -135,9 +138,22 @@ typedef struct {
    * handed over through the workspace with release/acquire flags.  Same arithmetic in the same order as the
    * single-level scan (bit-identical results); mutually exclusive with nseg > 1. */
   int chain_chunks;
+  /* Fused dt_proj (mamba_layer.py:1523).  0: the caller supplies delta / delta_tail.
+   * 32 / 48 / 80 (f16 / bf16 only): xdbl / xdbl_tail hold, after the 4*N B|C columns, the dt_proj INPUT of
+   * direction k in columns [4N + k*dt_rank_pad, 4N + (k+1)*dt_rank_pad) (rank zero-padded), and the kernel
+   * computes delta = dt_in @ w_dt[k]^T per 16-token tile with mma.sync (fp32 accumulate, one rounding to `dtype`,
+   * the rounding point of the reference's dts tensor).  Removes the delta tensors' HBM round trip. */
+  int dt_rank_pad;
 } actk_masked_scan_args;
 
 int actk_masked_scan_fwd(const actk_masked_scan_args *args, void *stream);
+
+/* Fused dt_proj weight image.  w: (2, D, R) `dtype` = dt_projs_weight of both directions (mamba_layer.py:1443),
+ * R <= dt_rank_pad in {32, 48, 80}.  img receives actk_dt_proj_image_bytes(D, dt_rank_pad, elsize) bytes: for every
+ * (direction, 64-channel block) the tensor-core A operand in shared-memory order, fetched by each CTA with one bulk
+ * copy.  Run once per weight load (the Python layer caches it per parameter version). */
+long long actk_dt_proj_image_bytes(int D, int dt_rank_pad, int elsize);
+int actk_pack_dt_proj_weight(const void *w, int D, int R, int dt_rank_pad, int dtype, void *img, void *stream);
 long long actk_masked_scan_workspace_bytes(const actk_masked_scan_args *args); /* host helper, 0 when nseg <= 1 */
 
 /* ---------------------------------------------------------------------------------------------

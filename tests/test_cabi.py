@@ -130,3 +130,40 @@ def test_workspace_and_gathered_layernorm_validation():
         == _status("ACTK_ERR_BAD_SHAPE")           # Ds % 8
     assert lib.actk_gathered_layernorm_fwd(1 << 20, 2, 10, 64, 1 << 20, 1 << 20, 1e-5, 1 << 20, 9, None) \
         == _status("ACTK_ERR_BAD_DTYPE")
+
+
+def test_fused_dt_proj_argument_validation():
+    """dt_rank_pad (fused dt_proj, header (2)): only f16/bf16, only the built slab counts, and xw must hold the columns."""
+    lib = _lib.load()
+    m = _lib.MaskedScanArgs()
+    m.dtype, m.n_branches, m.N, m.Bp, m.L, m.D, m.xw = _lib.ACTK_F32, 1, 16, 1, 64, 128, 128
+    m.dt_rank_pad = 32
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_DTYPE")
+    m.dtype, m.dt_rank_pad = _lib.ACTK_BF16, 64
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_UNSUPPORTED")
+    m.dt_rank_pad, m.xw = 48, 128
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_SHAPE")   # needs 64 + 96 columns
+    m.dt_rank_pad, m.xw = 32, 128
+    m.br[0].n_sel = 64                       # live branch without pointers
+    assert lib.actk_masked_scan_fwd(C.byref(m), None) == _status("ACTK_ERR_BAD_ARG")
+    assert b"NULL" in lib.actk_last_error()
+
+
+def test_derived_weight_layout_for_the_fused_dt_proj():
+    """x_proj rows are regrouped [B_0|C_0|B_1|C_1 | dt_0 | dt_1] with each direction's rank zero-padded to a 16-multiple
+    the in-kernel tcgen05.mma handles (20 -> 32, 40 -> 48, 80 -> 80)."""
+    import torch
+    from actalker_b200 import SS2D_Unit
+    from actalker_b200.mamba_layer import _rank_pad
+    assert [_rank_pad(r) for r in (4, 20, 32, 40, 80, 81)] == [(32, True), (32, True), (32, True), (48, True),
+                                                              (80, True), (88, False)]
+    u = SS2D_Unit(d_model=320, d_cond=64, cond_size=32, d_state=16, size=8, scan_type="sweep", num_direction=2)
+    dv = u.derived()
+    R, N, D, Rp = 20, 16, 640, 32
+    assert dv["xw"] == 4 * N + 2 * Rp and dv["rank_pad"] == Rp and dv["fusable"]
+    w = dv["w_xproj"]
+    for k in range(2):
+        assert torch.equal(w[k * 2 * N:(k + 1) * 2 * N], u.x_proj_weight[k, R:])
+        assert torch.equal(w[4 * N + k * Rp:4 * N + k * Rp + R], u.x_proj_weight[k, :R])
+        assert not w[4 * N + k * Rp + R:4 * N + (k + 1) * Rp].any()
+        assert torch.equal(dv["w_dt"][k * Rp:k * Rp + R, k * D:(k + 1) * D], u.dt_projs_weight[k].t())

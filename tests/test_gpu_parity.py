@@ -407,3 +407,50 @@ def test_layer_is_cuda_graph_capturable(cfg):
         with torch.no_grad():
             want = layer(x, idm, cd, masks)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("mode", ["single", "chain", "two_level"])
+@pytest.mark.parametrize("cfg", [(64, 20, 3), (320, 24, 2), (640, 12, 2), (1280, 10, 1), (96, 72, 25)])
+def test_fused_dt_proj_equals_gemm_route(dtype, cfg, mode):
+    """with 16-bit activations the scan kernel can compute dt_proj itself per 16-token tile
+    (tcgen05.mma into tensor memory, fp32 accumulate, one rounding to the activation dtype), in all three launch
+    shapes (single level, chained chunks, two-level).  Same contraction and rounding point as the cuBLAS GEMM
+    that otherwise writes the delta tensor, so the two routes may only differ where the fp32 sums round differently:
+    require agreement within one 16-bit rounding step of the layer output, on ragged masks, the id/cond tail, a
+    partial channel block (d_model 96 -> D = 192) and every rank slab count (dt_rank 4 / 20 / 40 / 80)."""
+    from actalker_b200 import SS2D_cond_v10, mamba_layer as ml
+    d_model, side, Bp = cfg
+    torch.manual_seed(21)
+    layer = SS2D_cond_v10(d_model=d_model, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=side,
+                          scan_type="sweep", num_direction=2).eval()
+    with torch.no_grad():
+        layer.exp_unit.A_logs.add_(0.3 * torch.randn_like(layer.exp_unit.A_logs))
+    layer = layer.to(dtype)
+    for n, p in layer.named_parameters():
+        if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias")):
+            p.data = p.data.float()
+    layer = layer.cuda()
+    assert layer.audio_unit.derived()["fusable"]
+    L = side * side
+    x = torch.randn(Bp, L, d_model, device="cuda").to(dtype)
+    idm = torch.randn(Bp, 1, 64, device="cuda").to(dtype)
+    cd = torch.randn(Bp, 33, 64, device="cuda").to(dtype)
+    rect = torch.zeros(1, 1, side * 8, side * 8, device="cuda", dtype=dtype)
+    rect[:, :, side: 7 * side, 2 * side: 6 * side + 3] = 1
+    masks = [torch.ones_like(rect), rect]
+    was = ml.FUSE_DT_PROJ
+    try:
+        ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = {"single": (1, 0), "chain": (1, 3), "two_level": (3, 0)}[mode]
+        with torch.no_grad():
+            ml.FUSE_DT_PROJ = False
+            want = layer(x, idm, cd, masks)
+            ml.FUSE_DT_PROJ = True
+            got = layer(x, idm, cd, masks)
+    finally:
+        ml.FUSE_DT_PROJ, ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = was, None, None
+    assert torch.isfinite(got.float()).all()
+    step = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    err = (got.float() - want.float()).abs()
+    assert (err <= step * (1.0 + want.float().abs())).all(), err.max()
+    assert (got == want).float().mean() > 0.97    # almost every output element is bit-identical

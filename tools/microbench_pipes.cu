@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(128) rate_kernel(float *out, const float *in, 
   const float a = in[17], b = in[18];
   const uint64_t a2 = pk(a, a), b2 = pk(b, b + 1e-3f);
   float acc = 0.f;
+  int n[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) n[i] = threadIdx.x * (i + 1);
+  const int kx = __float_as_int(a) | 5, ky = __float_as_int(b) | 3;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -32,6 +36,19 @@ __global__ void __launch_bounds__(128) rate_kernel(float *out, const float *in, 
         float4 x = *reinterpret_cast<const float4 *>(&sm[((it * 16 + i) * 4) & 1020]);
         acc += x.x + x.w;   // 2 FADD per LDS.128 (needed to keep the load alive)
       }
+      // mixes: does a packed op hold the dispatch port for both of its pipe cycles?
+      if (OP == 6) { v[i] = fma2(v[i], a2, b2); n[i] = (n[i] ^ kx) + ky; }                   // FFMA2 + LOP3 + IADD
+      if (OP == 7) { v[i] = fma2(v[i], a2, b2); if ((i & 3) == 0) f[i] = ex2(f[i]); }          // 4 FFMA2 : 1 MUFU
+      if (OP == 8) { f[i] = fmaf(f[i], a, b); f[(i + 8) & 15] = fmaf(f[(i + 8) & 15], a, b); n[i] = (n[i] ^ kx) + ky; }
+      if (OP == 9) { f[i] = ex2(f[i]); n[i] = (n[i] ^ kx) + ky; n[(i + 8) & 15] = (n[(i + 8) & 15] ^ ky) + kx; }  // MUFU + 4 ALU
+      if (OP == 10) {  // 3 FFMA2 : 1 LDS.128 (apply ratio), no FADD on the loaded data except one xor-reduce
+        v[i] = fma2(v[i], a2, b2);
+        if ((i % 3) == 0) {
+          float4 x = *reinterpret_cast<const float4 *>(&sm[((it * 16 + i) * 4) & 1020]);
+          n[i] ^= __float_as_int(x.x) ^ __float_as_int(x.w);
+        }
+      }
+      if (OP == 11) { v[i] = fma2(v[i], a2, b2); if ((i & 1) == 0) f[i] = ex2(f[i]); n[i] = (n[i] ^ kx) + ky; }  // 2 FFMA2 : 1 MUFU : 4 ALU
       if (OP == 5) {  // the apply() pattern: FMUL2 (bcast) + FFMA2 + FFMA2 per state pair, operands from registers
         uint64_t d = mul2(a2, v[(i + 1) & 15]);
         v[i] = fma2(b2, v[i], d);
@@ -41,7 +58,7 @@ __global__ void __launch_bounds__(128) rate_kernel(float *out, const float *in, 
   }
   float r = acc;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { float lo, hi; upk(v[i], lo, hi); r += f[i] + lo + hi; }
+  for (int i = 0; i < 16; ++i) { float lo, hi; upk(v[i], lo, hi); r += f[i] + lo + hi + __int_as_float(n[i]); }
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
@@ -76,5 +93,12 @@ int main() {
   run<3>("MUFU.EX2", 16, out, in);
   run<4>("LDS.128 broadcast (+2 FADD)", 16, out, in);
   run<5>("FMUL2+FFMA2+FFMA2 triple", 48, out, in);
+  // per GROUP of instructions (cycles for the whole group): a sum of the parts means the dispatch port is shared
+  run<6>("group{FFMA2,LOP3,IADD}", 16, out, in);
+  run<7>("group{4 FFMA2,1 MUFU}", 4, out, in);
+  run<8>("group{2 FFMA,LOP3,IADD}", 16, out, in);
+  run<9>("group{MUFU,2 LOP3,2 IADD}", 16, out, in);
+  run<10>("group{3 FFMA2,1 LDS.128,~2 LOP3}", 5, out, in);
+  run<11>("group{2 FFMA2,1 MUFU,2 LOP3,2 IADD}", 8, out, in);
   return cudaDeviceSynchronize() != cudaSuccess;
 }
