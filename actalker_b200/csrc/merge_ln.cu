@@ -25,6 +25,30 @@ __device__ __forceinline__ void load8(const T *p, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = IO<T>::ld(e + i);
   }
 }
+// raw 8-element vector (16 bytes of 16-bit data, 32 bytes of fp32) held in registers between load and use
+template <typename T>
+struct Raw8 {
+  uint4 w[sizeof(T) == 4 ? 2 : 1];
+};
+template <typename T>
+__device__ __forceinline__ Raw8<T> ldraw8(const T *p) {
+  Raw8<T> r;
+  r.w[0] = __ldcs(reinterpret_cast<const uint4 *>(p));
+  if (sizeof(T) == 4) r.w[sizeof(T) == 4 ? 1 : 0] = __ldcs(reinterpret_cast<const uint4 *>(p) + 1);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void unpack8(const Raw8<T> &r, float (&v)[8]) {
+  if (sizeof(T) == 4) {
+    const float *f = reinterpret_cast<const float *>(&r.w[0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = f[i];
+  } else {
+    const T *e = reinterpret_cast<const T *>(&r.w[0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = IO<T>::ld(e + i);
+  }
+}
 template <typename T>
 __device__ __forceinline__ void store8(T *p, const float (&v)[8]) {
   if (sizeof(T) == 4) {
@@ -51,37 +75,57 @@ __global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ M
   const size_t off = (size_t)row * D;
   const size_t dir1 = (size_t)rows * D;   // ydir[1] - ydir[0]
 
+  // The row flags are uniform over the warp, so every load address is known up front: all 16-byte loads of a chunk
+  // of up to 4 vectors per lane (x 2 branches x 2 directions) are issued before any arithmetic — the kernel is a
+  // pure HBM stream and was latency-bound with two loads in flight per lane (186 -> see DESIGN.md us at config 2).
+  bool sel[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) sel[br] = br < a.n_branches && a.selected[br][l] != 0;
+  constexpr int CH = VPL < 4 ? VPL : 4;
   float x[VPL][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-      float acc[8];
+  for (int i0 = 0; i0 < VPL; i0 += CH) {
+    Raw8<T> raw[CH][2][2];
+#pragma unroll
+    for (int ii = 0; ii < CH; ++ii) {
+      const int v = lane + 32 * (i0 + ii);
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        if (br >= a.n_branches) break;
-        float t[8];
-        if (a.selected[br][l]) {
-          float f[8], g[8];
-          const T *y0 = (const T *)a.ydir[br] + off + 8 * v;
-          load8(y0, f);
-          load8(y0 + dir1, g);
+        if (v < nvec && br < a.n_branches) {
+          const T *p = (sel[br] ? (const T *)a.ydir[br] : (const T *)a.xz[br]) + off + 8 * v;
+          raw[ii][br][0] = ldraw8(p);
+          if (sel[br]) raw[ii][br][1] = ldraw8(p + dir1);
+        }
+      }
+    }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(f[e] + g[e]);
-          if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
-            const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
+    for (int ii = 0; ii < CH; ++ii) {
+      const int i = i0 + ii, v = lane + 32 * i;
+      if (v < nvec) {
+        float acc[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
+        for (int br = 0; br < 2; ++br) {
+          if (br >= a.n_branches) break;
+          float t[8];
+          unpack8<T>(raw[ii][br][0], t);
+          if (sel[br]) {
+            float g[8];
+            unpack8<T>(raw[ii][br][1], g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] + g[e]);
+            if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
+              const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
+            }
           }
-        } else {
-          load8((const T *)a.xz[br] + off + 8 * v, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
+        for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
     }
   }
   if (!a.layernorm) {   // channel-sharded path: emit the merged sums, LayerNorm follows the all-gather
