@@ -63,6 +63,55 @@ class _timed:
         return False
 
 
+_SIDE_STREAMS = {}
+SIDE_STREAM = os.environ.get("ACTK_SIDE_STREAM", "1") != "0"
+
+
+class _Fork:
+    """Run the tiny id / condition-token GEMMs (a dozen ~4 us launches, ~55 us per call when serialised) on a side
+    stream beside the large in_proj / x_proj GEMMs of the latent tokens.  Fork: the side stream waits for the current
+    one; join: the current stream waits for the side stream and takes ownership of the results (record_stream), the
+    pattern CUDA-graph capture accepts."""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        if SIDE_STREAM:
+            key = (device.index if device.index is not None else torch.cuda.current_device())
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.side = _SIDE_STREAMS[key]
+        else:
+            self.side = None
+        self.wait = True
+
+    def __call__(self, wait: bool):
+        """`with fork(wait=False)`: re-enter the side stream WITHOUT waiting for what the current stream queued since
+        the first entry (only correct when the side work depends on nothing issued there in between)."""
+        self.wait = wait
+        return self
+
+    def __enter__(self):
+        if self.side is not None:
+            if self.wait:
+                self.side.wait_stream(self.main)
+            self.wait = True
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.side is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.main)
+
+
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -264,8 +313,10 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
             continue
         xw = dv["xw"]
         w_x = dv["w_xproj"].to(xz.dtype)
+        fork = _Fork(xz.device)
+        with fork:                                                         # tail tokens: side stream
+            xdbl_tail = F.linear(tail, w_x) if n_tail else None            # (Bp, n_tail, xw)
         xdbl = F.linear(xz, w_x)                                           # (Bp, L, xw)
-        xdbl_tail = F.linear(tail, w_x) if n_tail else None                # (Bp, n_tail, xw)
         A, Dsk, dtb = dv["A"], dv["Ds"], dv["dt_bias"]
         fused = FUSE_DT_PROJ and dv["fusable"] and xz.element_size() == 2
         w_dt = unit.dt_image(lo, hi, xz.dtype) if fused else dv["w_dt"].to(xz.dtype)
@@ -283,10 +334,12 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
                 dtr2d = xdbl.view(Bp * L, xw)[:, 4 * _N:]
             else:
                 dtr2d = xdbl[..., 4 * _N:].index_select(1, idx64s[i] if idx64s is not None else idxs[i].long()).reshape(Bp * n_sel, -1)
+            with fork(wait=sliced):    # sliced: w_dt was just cut on the current stream
+                delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
             delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)
-            delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
+        fork.join(xdbl_tail, delta_tail)
         # fused: the scan kernel multiplies each 16-token tile of dt columns by w_dt on the tensor cores itself
-        # (mma.sync, fp32 accumulate, one rounding to the activation dtype) — no delta tensor, no dt_proj launch
+        # (tcgen05.mma, fp32 accumulate, one rounding to the activation dtype) — no delta tensor, no dt_proj launch
         rp = dv["rank_pad"] if fused else 0
         if args.xw not in (0, xw) or (args.xw != 0 and args.dt_rank_pad != rp):
             raise RuntimeError("branches disagree on the x_proj width / dt rank")
@@ -382,17 +435,23 @@ class SS2D_cond_v10(nn.Module):
     def project_inputs(self, x, id_emb, conds, masks):
         """The dense front half of forward (mamba_layer.py:1958-1961, 1966, 1972, 1977): in_proj of both
         branches, id / condition projections, cached mask indices."""
+        if not x.is_cuda:
+            raise RuntimeError("actalker_b200 layers run on CUDA tensors only (no CPU path)")
         L = x.shape[1]
         audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
-        xz1 = self.in_proj1(x)
-        xz2 = self.in_proj2(x)
         m1 = self.mask_cache.get(masks[0], L)
         m2 = self.mask_cache.get(masks[1], L)
-        tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
-        if self.use_id:
-            id_tok = self.act2(self.id_proj(id_emb))
-            tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
-        return xz1.contiguous(), xz2.contiguous(), tail1.contiguous(), tail2.contiguous(), m1, m2
+        fork = _Fork(x.device)
+        with fork:                                   # 35 id / condition tokens per frame: side stream
+            tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
+            if self.use_id:
+                id_tok = self.act2(self.id_proj(id_emb))
+                tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
+            tail1, tail2 = tail1.contiguous(), tail2.contiguous()
+        xz1 = self.in_proj1(x)                       # the latent tokens: current stream
+        xz2 = self.in_proj2(x)
+        fork.join(tail1, tail2)
+        return xz1.contiguous(), xz2.contiguous(), tail1, tail2, m1, m2
 
     def _check_forward_only(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
