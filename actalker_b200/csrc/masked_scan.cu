@@ -394,6 +394,10 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   const int ch = k * D + d0 + (live ? tid : 0);
   ChannelScan<POWER_A> cs;
   cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
+  // ring slots and y double-buffer are indexed by the tile number relative to the chunk start.  The first tiles are
+  // requested BEFORE a chained chunk waits for its predecessor's state: their HBM latency overlaps the wait.
+  for (int t = t_begin; t < min(t_begin + S - 1, t_end); ++t) issue_load(t, geo(t));
+
   if (MODE == 0 && seg > 0 && live) {
     const float *h0 = P.ws_h0 + (ws_row + tid) * kN;
 #pragma unroll
@@ -418,8 +422,6 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   }
   float sumdt = 0.f;
 
-  // ring slots and y double-buffer are indexed by the tile number relative to the chunk start
-  for (int t = t_begin; t < min(t_begin + S - 1, t_end); ++t) issue_load(t, geo(t));
 
   if constexpr (kFused) {
     if (t_begin < t_end) issue_mma(t_begin);
