@@ -19,7 +19,7 @@ ABI_VERSION = 7
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
-           "actk_pack_dt_proj_weight", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
+           "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
            "actk_scan_algorithmic_bytes"]
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -99,13 +99,17 @@ def load():
     lib.actk_pack_dt_proj_weight.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
     lib.actk_pack_dt_proj_weight.restype = _i
     lib.actk_merge_layernorm_fwd.argtypes = [C.POINTER(MergeLnArgs), _vp]
+    lib.actk_merge_ln_outproj_supported.argtypes = [_i, _i, _i]
+    lib.actk_merge_ln_outproj_supported.restype = _i
+    lib.actk_merge_ln_outproj_fwd.argtypes = [C.POINTER(MergeLnArgs), _vp, _vp, _i, _vp]
+    lib.actk_merge_ln_outproj_fwd.restype = _i
     lib.actk_a_structure.argtypes = [_vp, _i, _i, _f, _vp, _vp]
     lib.actk_gathered_layernorm_fwd.argtypes = [_vp, _i, _ll, _i, _vp, _vp, _f, _vp, _i, _vp]
     lib.actk_gathered_layernorm_fwd.restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll
     for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
-           "actk_pack_dt_proj_weight", "actk_merge_layernorm_fwd", "actk_a_structure"):
+           "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_a_structure"):
         getattr(lib, name).restype = _i
     if lib.actk_abi_version() != ABI_VERSION:
         raise LibraryMissing(f"{path}: ABI version {lib.actk_abi_version()} != {ABI_VERSION}; rebuild")

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libactalker_b200.so")
-SOURCES = ["api.cu", "masked_scan.cu", "selective_scan.cu", "merge_ln.cu"]
+SOURCES = ["api.cu", "masked_scan.cu", "selective_scan.cu", "merge_ln.cu", "ln_outproj.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--use_fast_math", "-Xcompiler", "-fPIC",

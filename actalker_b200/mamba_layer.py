@@ -63,6 +63,11 @@ class _timed:
         return False
 
 
+# merge + LayerNorm + out_proj as one tcgen05 kernel where the shape is built (D = 640, 16-bit).
+# Off by default (ACTK_FUSE_LN_OUT=1 turns it on): measured on B200 at config 2 it takes 0.46 ms against 0.16 + 0.04 ms
+# for the merge kernel + cuBLAS GEMM — one CTA per SM around a 160 KB operand tile cannot keep enough HBM loads in
+# flight while it normalises rows.
+FUSE_LN_OUT_PROJ = os.environ.get("ACTK_FUSE_LN_OUT", "0") == "1"
 _SIDE_STREAMS = {}
 SIDE_STREAM = os.environ.get("ACTK_SIDE_STREAM", "1") != "0"
 
@@ -403,11 +408,13 @@ class SS2D_cond_v10(nn.Module):
         self.mask_cache = MaskIndexCache()
 
     def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None, weights=None,
-                  layernorm=None):
+                  layernorm=None, out_proj=False):
         """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
         ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
         ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
-        LayerNorm needs every channel and runs after the all-gather (sharded.py)."""
+        LayerNorm needs every channel and runs after the all-gather (sharded.py).
+        out_proj=True: also apply out_proj and return (Bp, L, d_model) — fused into one tcgen05 kernel with the merge
+        and LayerNorm where the shape is built (actk_merge_ln_outproj_supported), else merge kernel + cuBLAS."""
         lib = _lib.load()
         Bp, L, D = xz1.shape
         res = _scan_branches([self.audio_unit, self.exp_unit], [xz1, xz2], [tail1, tail2], [m1.idx, m2.idx],
@@ -426,9 +433,18 @@ class SS2D_cond_v10(nn.Module):
             gamma, beta = self.out_norm.weight.to(xz1.dtype), self.out_norm.bias.to(xz1.dtype)
             a.gamma, a.beta = _ptr(gamma), _ptr(beta)
         a.eps, a.n_branches, a.Bp, a.L, a.D, a.dtype = self.out_norm.eps, 2, Bp, L, Dk, _DTYPES[xz1.dtype]
+        w_out = self.out_proj.weight
+        if (out_proj and a.layernorm and FUSE_LN_OUT_PROJ and self.out_proj.bias is None and w_out.dtype == xz1.dtype
+                and lib.actk_merge_ln_outproj_supported(Dk, w_out.shape[0], a.dtype)):
+            y = torch.empty((Bp, L, w_out.shape[0]), dtype=xz1.dtype, device=xz1.device)
+            w_c = w_out if w_out.is_contiguous() else w_out.contiguous()
+            with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
+                _lib.check(lib.actk_merge_ln_outproj_fwd(ct.byref(a), _ptr(w_c), _ptr(y), w_out.shape[0], _stream(xz1)),
+                           "actk_merge_ln_outproj_fwd")
+            return y
         with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
-        return out
+        return self.out_proj(out) if out_proj else out
 
     use_id = True   # SS2D_cond_v10_wo_id drops the identity token (and has no id_proj)
 
@@ -462,8 +478,7 @@ class SS2D_cond_v10(nn.Module):
         # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
         # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
         self._check_forward_only(x)
-        y = self.scan_core(*self.project_inputs(x, id_emb, conds, masks))
-        return self.out_proj(y)
+        return self.scan_core(*self.project_inputs(x, id_emb, conds, masks), out_proj=True)
 
 
 class SS2D_cond_v10_wo_id(SS2D_cond_v10):
@@ -487,14 +502,15 @@ class SS2D_cond_v8(SS2D_cond_v10):
     and condition tail), each result is multiplied by its bicubically downsampled mask (:1777-1797), the two are
     added, then out_norm / out_proj.  Same parameters as v10; same kernels with per-row weights in the merge."""
 
-    def _blend(self, x, id_emb, conds, masks, layernorm):
+    def _blend(self, x, id_emb, conds, masks, layernorm, out_proj=False):
         self._check_forward_only(x)
         xz1, xz2, tail1, tail2, m1, m2 = self.project_inputs(x, id_emb, conds, masks)
         f1, f2 = _full_index(m1, x.device), _full_index(m2, x.device)
-        return self.scan_core(xz1, xz2, tail1, tail2, f1, f2, weights=[m1.weight, m2.weight], layernorm=layernorm)
+        return self.scan_core(xz1, xz2, tail1, tail2, f1, f2, weights=[m1.weight, m2.weight], layernorm=layernorm,
+                              out_proj=out_proj)
 
     def forward(self, x, id_emb, conds, masks):
-        return self.out_proj(self._blend(x, id_emb, conds, masks, layernorm=True))
+        return self._blend(x, id_emb, conds, masks, layernorm=True, out_proj=True)
 
 
 class SS2D_cond_v9(SS2D_cond_v8):

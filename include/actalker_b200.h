@@ -185,6 +185,15 @@ typedef struct {
 
 int actk_merge_layernorm_fwd(const actk_merge_ln_args *args, void *stream);
 
+/* (3a) The same merge + LayerNorm followed by out_proj (mamba_layer.py:1985, nn.Linear(D, d_model, bias=False)) in one
+ *      kernel: 128-row tiles are normalised straight into the tensor cores' shared-memory operand
+ *      and multiplied by w_out (d_model, D) `dtype` row-major with tcgen05.mma (fp32 accumulate, one rounding);
+ *      out (Bp*L, d_model).  args->out is ignored, args->layernorm is taken as 1.  Built for f16 / bf16, D == 640,
+ *      d_model % 32 == 0 and <= 512 (actk_merge_ln_outproj_supported); other shapes return ACTK_ERR_UNSUPPORTED and
+ *      the caller runs (3) plus a library GEMM. */
+int actk_merge_ln_outproj_supported(int D, int d_model, int dtype);
+int actk_merge_ln_outproj_fwd(const actk_merge_ln_args *args, const void *w_out, void *out, int d_model, void *stream);
+
 /* (3b) LayerNorm over channel slices gathered from `parts` ranks (the layout an NCCL all-gather of per-rank
  *      (rows, Ds) buffers produces): in (parts, rows, Ds) -> out (rows, parts*Ds), statistics in fp32 over all
  *      parts*Ds channels (mamba_layer.py:1984 needs complete channels).  Ds % 8 == 0, parts*Ds <= 8192. */

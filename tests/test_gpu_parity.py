@@ -454,3 +454,47 @@ def test_fused_dt_proj_equals_gemm_route(dtype, cfg, mode):
     err = (got.float() - want.float()).abs()
     assert (err <= step * (1.0 + want.float().abs())).all(), err.max()
     assert (got == want).float().mean() > 0.97    # almost every output element is bit-identical
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cfg", [(18, 3, "v10"), (24, 2, "v10"), (13, 5, "v10"), (16, 2, "v8"), (72, 25, "v10")])
+def test_fused_ln_out_proj_equals_unfused_route(dtype, cfg):
+    """merge + LayerNorm + out_proj as one tcgen05 kernel (D = 640) against the merge kernel + cuBLAS
+    route.  Both round the normalised tensor to the activation dtype and accumulate the projection in fp32, so they
+    may differ only by fp32 summation order before the final rounding: agreement within one rounding step of the
+    output, on partial row tiles (B'L % 128 != 0), rectangle masks (pass-through rows) and the v8 row weights."""
+    from actalker_b200 import SS2D_cond_v10, SS2D_cond_v8, mamba_layer as ml
+    side, Bp, kind = cfg
+    torch.manual_seed(33)
+    cls = SS2D_cond_v8 if kind == "v8" else SS2D_cond_v10
+    layer = cls(d_model=320, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=side, scan_type="sweep",
+                num_direction=2).eval()
+    with torch.no_grad():
+        layer.out_norm.weight.add_(0.2 * torch.randn_like(layer.out_norm.weight))
+        layer.out_norm.bias.add_(0.2 * torch.randn_like(layer.out_norm.bias))
+    layer = layer.to(dtype)
+    for n, p in layer.named_parameters():
+        if any(s in n for s in ("A_logs", "Ds", "dt_projs_bias")):
+            p.data = p.data.float()
+    layer = layer.cuda()
+    L = side * side
+    x = torch.randn(Bp, L, 320, device="cuda").to(dtype)
+    idm = torch.randn(Bp, 1, 64, device="cuda").to(dtype)
+    cd = torch.randn(Bp, 33, 64, device="cuda").to(dtype)
+    rect = torch.zeros(1, 1, side * 8, side * 8, device="cuda", dtype=dtype)
+    rect[:, :, side: 7 * side, 2 * side: 6 * side + 3] = 1
+    masks = [torch.ones_like(rect), rect]
+    was = ml.FUSE_LN_OUT_PROJ
+    try:
+        with torch.no_grad():
+            ml.FUSE_LN_OUT_PROJ = False
+            want = layer(x, idm, cd, masks)
+            ml.FUSE_LN_OUT_PROJ = True
+            got = layer(x, idm, cd, masks)
+    finally:
+        ml.FUSE_LN_OUT_PROJ = was
+    assert got.shape == want.shape and torch.isfinite(got.float()).all()
+    step = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    err = (got.float() - want.float()).abs()
+    assert (err <= step * (1.0 + want.float().abs())).all(), err.max()
+    assert (got == want).float().mean() > 0.9
