@@ -315,6 +315,31 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       const int cu = nch / kPer, cb = 2 * kN / kPer;       // pieces per u row, per B|C row
       const int cd = kFused ? RP / kPer : cu;              // pieces per dt-input row (fused) / delta row
       const int per_row = cu + cd + cb;
+      if (nch == kCh) {
+        // full channel block: four threads per tile row, fixed pieces per thread — one index lookup per thread and
+        // no divisions (mask edges make a third to two thirds of the tiles ragged under rectangle masks)
+        constexpr int CU = kCh / kPer, CB = 2 * kN / kPer, CD = kFused ? RP / kPer : CU;
+        const int jj = tid >> 2, q = tid & 3;
+        if (jj < g.nrows) {
+          const int l = g.l_lo + jj, j = l - g.l_first;
+          const T *usrc, *bsrc;
+          src_rows(l, usrc, bsrc);
+#pragma unroll
+          for (int i = 0; i < CU / 4; ++i) cp_async16(&sg.u[j][(q + 4 * i) * kPer], usrc + (q + 4 * i) * kPer);
+          if constexpr (kFused) {
+#pragma unroll
+            for (int i = 0; i < (CD + 3) / 4; ++i)
+              if (q + 4 * i < CD) cp_async16(&sg.dtin[q + 4 * i][j][0], bsrc + 4 * kN + k * RP + (q + 4 * i) * kPer);
+          } else {
+            const T *dsrc = (l < n_sel ? br.delta + (((size_t)b * n_sel + l) * 2 + k) * D
+                                       : br.delta_tail + (((size_t)b * n_tail + (l - n_sel)) * 2 + k) * D) + d0;
+#pragma unroll
+            for (int i = 0; i < CU / 4; ++i) cp_async16(&sg.dt[j][(q + 4 * i) * kPer], dsrc + (q + 4 * i) * kPer);
+          }
+#pragma unroll
+          for (int i = 0; i < CB / 4; ++i) cp_async16(&sg.bc[j][(q + 4 * i) * kPer], bsrc + k * 2 * kN + (q + 4 * i) * kPer);
+        }
+      } else
       for (int id = tid; id < g.nrows * per_row; id += kCh) {
         const int jj = id / per_row, w = id - jj * per_row;
         const int l = g.l_lo + jj, j = l - g.l_first;
@@ -378,6 +403,18 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     } else {
       constexpr int kPer = 16 / sizeof(T);
       const int cu = nch / kPer;
+      if (nch == kCh) {   // four threads per tile row, fixed pieces (see issue_load)
+        constexpr int CU = kCh / kPer;
+        const int jj = tid >> 2, q = tid & 3, l = g.l_lo + jj;
+        if (jj < g.nrows && l < n_sel) {
+          const int row = br.idx_iota ? l : __ldg(br.idx + l);
+#pragma unroll
+          for (int i = 0; i < CU / 4; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&ybuf[(t - t_begin) & 1][l - g.l_first][(q + 4 * i) * kPer]);
+            *reinterpret_cast<uint4 *>(ydst + (size_t)row * D + (q + 4 * i) * kPer) = v;
+          }
+        }
+      } else
       for (int id = tid; id < g.nrows * cu; id += kCh) {
         const int jj = id / cu, w = id - jj * cu;
         const int l = g.l_lo + jj;
