@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       const int row = br.idx_iota ? l : __ldg(br.idx + l);
       const size_t tok = (size_t)b * L + row;
       usrc = br.xz + tok * D + d0;
-      bsrc = br.xdbl + tok * P.xw;
+      bsrc = br.xdbl + ((size_t)b * n_sel + l) * P.xw;     // x_dbl of the selected tokens is in sequence order
     } else {
       const size_t tok = (size_t)b * n_tail + (l - n_sel);
       usrc = br.tail + tok * D + d0;
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     if (g.fast) {
       if (tid == kTmaTid) {
         mbar_expect_tx(bar, (uint32_t)sizeof(Stage<T, KS>));
-        if constexpr (kFused) tma_load_4d(&sg.dtin[0][0][0], &maps.xdbl_dt, 0, g.row0, (4 * kN + k * RP) / 8, b, bar);
+        if constexpr (kFused) tma_load_4d(&sg.dtin[0][0][0], &maps.xdbl_dt, 0, g.l_first, (4 * kN + k * RP) / 8, b, bar);
         else tma_load_3d(&sg.dt[0][0], &maps.delta, k * D + d0, g.l_first, b, bar);
         tma_load_3d(&sg.u[0][0], &maps.xz, d0, g.row0, b, bar);
-        tma_load_3d(&sg.bc[0][0], &maps.xdbl, k * 2 * kN, g.row0, b, bar);
+        tma_load_3d(&sg.bc[0][0], &maps.xdbl, k * 2 * kN, g.l_first, b, bar);
       }
       mbar_arrive(bar);
     } else {
@@ -784,9 +784,9 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
       const uint64_t Lp = (uint64_t)s.n_sel + s.n_tail;
       int rc;
       if ((rc = make_map(&M.m[i].xz, dt, es, s.xz, a->D, a->L, a->Bp, kCh))) return rc;
-      if ((rc = make_map(&M.m[i].xdbl, dt, es, s.xdbl, a->xw, a->L, a->Bp, 2 * kN))) return rc;
+      if ((rc = make_map(&M.m[i].xdbl, dt, es, s.xdbl, a->xw, (uint64_t)s.n_sel, a->Bp, 2 * kN))) return rc;
       if (ks) {
-        if ((rc = make_map_dtin(&M.m[i].xdbl_dt, dt, es, s.xdbl, a->xw, a->L, a->Bp, 16 * ks))) return rc;
+        if ((rc = make_map_dtin(&M.m[i].xdbl_dt, dt, es, s.xdbl, a->xw, (uint64_t)s.n_sel, a->Bp, 16 * ks))) return rc;
       } else if ((rc = make_map(&M.m[i].delta, dt, es, s.delta, 2ull * a->D, (uint64_t)s.n_sel, a->Bp, kCh))) return rc;
       if ((rc = make_map(&M.m[i].ydir, dt, es, s.ydir, a->D, a->L, 2ull * a->Bp, kCh))) return rc;
     }

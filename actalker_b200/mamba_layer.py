@@ -75,8 +75,7 @@ SIDE_STREAM = os.environ.get("ACTK_SIDE_STREAM", "1") != "0"
 class _Fork:
     """Run the tiny id / condition-token GEMMs (a dozen ~4 us launches, ~55 us per call when serialised) on a side
     stream beside the large in_proj / x_proj GEMMs of the latent tokens.  Fork: the side stream waits for the current
-    one; join: the current stream waits for the side stream and takes ownership of the results (record_stream), the
-    pattern CUDA-graph capture accepts."""
+    one; join: the current stream waits for the side stream — the pattern CUDA-graph capture accepts."""
 
     def __init__(self, device):
         self.main = torch.cuda.current_stream(device)
@@ -110,11 +109,12 @@ class _Fork:
         return False
 
     def join(self, *tensors):
+        # No record_stream on the results: it defers the allocator's reuse of those blocks behind event queries and
+        # produced sporadic cudaMalloc stalls (~1 ms) in the layer loop.  It is not needed here: side-stream blocks are
+        # only ever re-used by side-stream work, and every fork starts by waiting for everything the current stream
+        # has queued — including the kernels that read these results.
         if self.side is not None:
             self.main.wait_stream(self.side)
-            for t in tensors:
-                if t is not None:
-                    t.record_stream(self.main)
 
 
 def _pad8(n: int) -> int:
@@ -321,7 +321,17 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         fork = _Fork(xz.device)
         with fork:                                                         # tail tokens: side stream
             xdbl_tail = F.linear(tail, w_x) if n_tail else None            # (Bp, n_tail, xw)
-        xdbl = F.linear(xz, w_x)                                           # (Bp, L, xw)
+        # x_proj of the SELECTED tokens only, in sequence order (row p <-> latent token idx[p]).  Under a partial mask
+        # the rows are gathered first when few are selected (the GEMM shrinks with them), else projected in place and
+        # the narrow x_dbl rows gathered afterwards.
+        if n_sel == L:
+            xdbl = F.linear(xz, w_x)                                       # (Bp, L, xw)
+        else:
+            sel64 = idx64s[i] if idx64s is not None else idxs[i].long()
+            if 2 * n_sel <= L:
+                xdbl = F.linear(xz.index_select(1, sel64), w_x)            # (Bp, n_sel, xw)
+            else:
+                xdbl = F.linear(xz, w_x).index_select(1, sel64)
         A, Dsk, dtb = dv["A"], dv["Ds"], dv["dt_bias"]
         fused = FUSE_DT_PROJ and dv["fusable"] and xz.element_size() == 2
         w_dt = unit.dt_image(lo, hi, xz.dtype) if fused else dv["w_dt"].to(xz.dtype)
@@ -335,10 +345,7 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
             # dt_proj as one GEMM over both directions (block-diagonal weight).  The dt columns of x_dbl are read in
             # place as a strided 2-D operand (lda = xw): no copy of the (Bp*L, 2Rp) slice, and the tail rows get their
             # own small GEMM instead of a concatenation.  Rows are in sequence order: row p <-> latent token idx[p].
-            if n_sel == L:
-                dtr2d = xdbl.view(Bp * L, xw)[:, 4 * _N:]
-            else:
-                dtr2d = xdbl[..., 4 * _N:].index_select(1, idx64s[i] if idx64s is not None else idxs[i].long()).reshape(Bp * n_sel, -1)
+            dtr2d = xdbl.view(Bp * n_sel, xw)[:, 4 * _N:]
             with fork(wait=sliced):    # sliced: w_dt was just cut on the current stream
                 delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
             delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)

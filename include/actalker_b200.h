@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 7
+#define ACTK_ABI_VERSION 8
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -92,7 +92,8 @@ int actk_selective_scan_fwd(const actk_scan_args *args, void *stream);
  *                                 row idx[p]
  *   tail      : (Bp, n_tail, D)   id token followed by the projected condition tokens
  *                                 (sequence positions n_sel .. n_sel+n_tail-1)
- *   xdbl      : (Bp, L, xw)       x_proj output of the latent tokens; columns [0, 4*N) hold
+ *   xdbl      : (Bp, n_sel, xw)   x_proj output of the SELECTED tokens in sequence order (row p <-> token idx[p];
+ *                                 with an all-ones mask that is simply (Bp, L, xw)); columns [0, 4*N) hold
  *                                 [B_dir0 | C_dir0 | B_dir1 | C_dir1]; xw*elsize % 16 == 0
  *   xdbl_tail : (Bp, n_tail, xw)  same for the tail tokens
  *   delta     : (Bp, n_sel, 2*D)  dt_proj output of the selected tokens in SEQUENCE order (row p <-> token idx[p]);
