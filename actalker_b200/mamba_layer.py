@@ -273,11 +273,13 @@ def auto_chain(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
 
 
 def auto_segments(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
-    """Chunks per sequence for the two-level scan.  One chunk (single level, no extra work) whenever the
-    independent (batch x branch x direction x channel-block) axes already give every SM ~4 CTAs; otherwise cut time
-    so that about 6 CTAs per SM exist, keeping chunks >= 8 tiles (128 steps) so the 75 % extra state-only pass and
-    the carry stay a small price for the parallelism (BASELINE config 5, single-frame calls)."""
-    if n_ctas >= 4 * n_sms or min_tiles < 16:
+    """Chunks per sequence for the two-level scan.  The extra state-only pass costs ~75 % more work, so cutting time
+    only pays when the independent (batch x branch x direction x channel-block) axes leave warp schedulers EMPTY:
+    about one 2-warp CTA per SM or fewer (single-frame calls, BASELINE config 5's one long sequence).  From one CTA per
+    SM upwards a single level is faster even at low occupancy — measured on B200 for the channel-sharded slices of
+    config 2: 500 CTAs 1.02 ms single level vs 1.74 ms in two segments, 300 CTAs 1.01 vs 1.16, 200 CTAs 0.70 vs 0.90
+    (tools/bench_sliced.py).  When it does cut, it aims at about 6 CTAs per SM with chunks of >= 8 tiles."""
+    if n_ctas >= 5 * n_sms // 4 or min_tiles < 16:    # 160 CTAs (B'=4 at 72x72): two levels 0.75 vs 0.84 ms per call
         return 1
     return max(1, min(-(-6 * n_sms // n_ctas), min_tiles // 8))
 

@@ -324,6 +324,7 @@ def test_small_batch_long_sequence_picks_two_level_scan_and_matches_oracle():
     assert auto_segments(1000, 327) == 1                    # config 2: 1000 CTAs -> single level
     assert auto_segments(40, 32400) == 23                   # config 5 flattened, one sequence
     assert auto_segments(40, 12) == 1                       # too short to cut
+    assert auto_segments(500, 327) == 1                     # a rank's half of d_inner: single level is faster
     torch.manual_seed(9)
     side = 48
     kw = dict(d_model=32, d_cond=64, cond_size=32, dropout=0.1, d_state=16, size=side, scan_type="sweep",
