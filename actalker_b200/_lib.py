@@ -15,12 +15,13 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
            "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
-           "actk_scan_algorithmic_bytes"]
+           "actk_scan_algorithmic_bytes", "actk_peer_buffer_alloc", "actk_peer_buffer_free", "actk_peer_buffer_export",
+           "actk_peer_buffer_open", "actk_peer_buffer_close"]
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -53,7 +54,7 @@ class MergeLnArgs(C.Structure):
     _fields_ = [("xz", _vp * 2), ("ydir", _vp * 2), ("selected", _vp * 2),
                 ("gamma", _vp), ("beta", _vp), ("out", _vp), ("eps", _f),
                 ("n_branches", _i), ("Bp", _i), ("L", _i), ("D", _i), ("dtype", _i), ("layernorm", _i),
-                ("row_weight", _vp * 2)]
+                ("row_weight", _vp * 2), ("peer_out", _vp * 8), ("n_peers", _i), ("my_part", _i)]
 
 
 class LibraryMissing(RuntimeError):
@@ -106,6 +107,14 @@ def load():
     lib.actk_a_structure.argtypes = [_vp, _i, _i, _f, _vp, _vp]
     lib.actk_gathered_layernorm_fwd.argtypes = [_vp, _i, _ll, _i, _vp, _vp, _f, _vp, _i, _vp]
     lib.actk_gathered_layernorm_fwd.restype = _i
+    lib.actk_peer_buffer_alloc.argtypes = [_ll, C.POINTER(_vp)]
+    lib.actk_peer_buffer_export.argtypes = [_vp, C.c_char_p]
+    lib.actk_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(_vp)]
+    lib.actk_peer_buffer_free.argtypes = [_vp]
+    lib.actk_peer_buffer_close.argtypes = [_vp]
+    for name in ("actk_peer_buffer_alloc", "actk_peer_buffer_export", "actk_peer_buffer_open", "actk_peer_buffer_free",
+                 "actk_peer_buffer_close"):
+        getattr(lib, name).restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll
     for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",

@@ -1,6 +1,7 @@
 // C-ABI housekeeping: error text, version, A-structure probe, algorithmic-bytes helper.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -42,6 +43,38 @@ extern "C" int actk_a_structure(const float *A, int dim, int dstate, float rel_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   a_structure_kernel<<<1, 1024, 0, st>>>(A, dim, dstate, rel_tol, flag_dev);
   ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
+}
+
+// ---- gather buffers of the fused push all-gather (multi-GPU channel sharding, one process per GPU) -----------------
+// Plain cudaMalloc allocations exported / imported with CUDA IPC: the importer maps a peer's buffer into ITS device's
+// address space with peer access enabled, so the merge kernel can store into it over NVLink.
+extern "C" int actk_peer_buffer_alloc(long long bytes, void **ptr) {
+  if (!ptr || bytes <= 0) ACTK_FAIL(ACTK_ERR_BAD_ARG, "peer_buffer_alloc: bytes=%lld", bytes);
+  ACTK_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
+  return ACTK_OK;
+}
+extern "C" int actk_peer_buffer_free(void *ptr) {
+  ACTK_CUDA_OK(cudaFree(ptr));
+  return ACTK_OK;
+}
+extern "C" int actk_peer_buffer_export(void *ptr, unsigned char *handle64) {
+  if (!ptr || !handle64) ACTK_FAIL(ACTK_ERR_BAD_ARG, "peer_buffer_export: NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  ACTK_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return ACTK_OK;
+}
+extern "C" int actk_peer_buffer_open(const unsigned char *handle64, void **ptr) {
+  if (!ptr || !handle64) ACTK_FAIL(ACTK_ERR_BAD_ARG, "peer_buffer_open: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  ACTK_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ACTK_OK;
+}
+extern "C" int actk_peer_buffer_close(void *ptr) {
+  ACTK_CUDA_OK(cudaIpcCloseMemHandle(ptr));
   return ACTK_OK;
 }
 

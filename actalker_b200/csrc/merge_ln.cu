@@ -129,6 +129,18 @@ __global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ M
     }
   }
   if (!a.layernorm) {   // channel-sharded path: emit the merged sums, LayerNorm follows the all-gather
+    if (a.n_peers > 0) {
+      // fused push all-gather: this rank's slice goes straight into every rank's gather buffer over NVLink (16-byte
+      // peer stores), in the (part, row, slice) layout gathered_ln_kernel reads — no separate collective launch
+      const size_t poff = ((size_t)a.my_part * rows + row) * D;
+      for (int p = 0; p < a.n_peers; ++p) {
+        T *dst = (T *)a.peer_out[p] + poff;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          if (lane + 32 * i < nvec) store8(dst + 8 * (lane + 32 * i), x[i]);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
       if (lane + 32 * i < nvec) store8((T *)a.out + off + 8 * (lane + 32 * i), x[i]);
@@ -248,7 +260,13 @@ extern "C" int actk_merge_layernorm_fwd(const actk_merge_ln_args *a, void *strea
   if (a->n_branches < 1 || a->n_branches > 2) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: n_branches=%d", a->n_branches);
   if (a->Bp <= 0 || a->L <= 0 || a->D <= 0 || a->D % 8 != 0 || a->D > 8192)
     ACTK_FAIL(ACTK_ERR_BAD_SHAPE, "merge_ln: Bp=%d L=%d D=%d (D must be a multiple of 8, <= 8192)", a->Bp, a->L, a->D);
-  if (!a->out || (a->layernorm && (!a->gamma || !a->beta)))
+  if (a->n_peers < 0 || a->n_peers > 8 || (a->n_peers > 0 && (a->layernorm || a->my_part < 0 || a->my_part >= a->n_peers)))
+    ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: n_peers=%d my_part=%d layernorm=%d (push gather needs layernorm == 0, my_part < n_peers <= 8)",
+              a->n_peers, a->my_part, a->layernorm);
+  for (int p = 0; p < a->n_peers; ++p)
+    if (!a->peer_out[p] || (reinterpret_cast<uintptr_t>(a->peer_out[p]) & 15))
+      ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: peer_out[%d] is NULL or not aligned to 16 bytes", p);
+  if ((!a->out && a->n_peers == 0) || (a->layernorm && (!a->gamma || !a->beta)))
     ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: out (and gamma, beta when layernorm != 0) are required");
   for (int i = 0; i < a->n_branches; ++i) {
     if (!a->xz[i] || !a->ydir[i] || !a->selected[i]) ACTK_FAIL(ACTK_ERR_BAD_ARG, "merge_ln: branch %d has a NULL pointer", i);

@@ -417,24 +417,31 @@ class SS2D_cond_v10(nn.Module):
         self.mask_cache = MaskIndexCache()
 
     def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None, weights=None,
-                  layernorm=None, out_proj=False):
+                  layernorm=None, out_proj=False, push=None):
         """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
         ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
         ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
         LayerNorm needs every channel and runs after the all-gather (sharded.py).
         out_proj=True: also apply out_proj and return (Bp, L, d_model) — fused into one tcgen05 kernel with the merge
-        and LayerNorm where the shape is built (actk_merge_ln_outproj_supported), else merge kernel + cuBLAS."""
+        and LayerNorm where the shape is built (actk_merge_ln_outproj_supported), else merge kernel + cuBLAS.
+        push=(peer_ptrs, my_part) with ch_slice: the merged slice is written straight into every rank's gather buffer
+        over NVLink peer memory instead of a local tensor (sharded.py, gather="p2p"); returns None."""
         lib = _lib.load()
         Bp, L, D = xz1.shape
         res = _scan_branches([self.audio_unit, self.exp_unit], [xz1, xz2], [tail1, tail2], [m1.idx, m2.idx],
                              [m1.n_sel, m2.n_sel], Bp, L, idx64s=[m1.idx64, m2.idx64], ch_slice=ch_slice)
         Dk = res[0][1].shape[-1]
-        out = torch.empty((Bp, L, Dk), dtype=xz1.dtype, device=xz1.device)
+        out = None if push is not None else torch.empty((Bp, L, Dk), dtype=xz1.dtype, device=xz1.device)
         a = _lib.MergeLnArgs()
         for i, ((yd, xz_k), m) in enumerate(zip(res, (m1, m2))):
             a.xz[i], a.ydir[i], a.selected[i] = xz_k.data_ptr(), yd.data_ptr(), m.selected.data_ptr()
         a.out = _ptr(out)
         a.layernorm = (1 if ch_slice is None else 0) if layernorm is None else int(layernorm)
+        if push is not None:
+            ptrs, a.my_part = push
+            a.n_peers = len(ptrs)
+            for p_i, ptr in enumerate(ptrs):
+                a.peer_out[p_i] = ptr
         if weights is not None:                      # v8 / v9: multiplicative blend with the downsampled masks
             wts = [w.to(xz1.dtype).contiguous() for w in weights]
             a.row_weight[0], a.row_weight[1] = wts[0].data_ptr(), wts[1].data_ptr()

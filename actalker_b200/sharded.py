@@ -73,14 +73,84 @@ def all_gather_slices(local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+class PeerGatherBuffers:
+    """Gather buffers for the fused push all-gather (gather="p2p"): every rank owns `depth` buffers of
+    (world, rows, Ds) elements (plain cudaMalloc, C-ABI actk_peer_buffer_*) and maps every other rank's buffers into
+    its own device's address space through CUDA IPC, so the merge kernel can store its slice into all of them over
+    NVLink.
+
+    Ordering: call i writes buffer i % depth on every rank, then a stream-ordered 4-byte all-reduce separates the
+    writers from the readers (a rank's reduction kernel starts after its own merge kernel, and completes only once
+    every rank has joined).  With depth 2 a buffer is rewritten two calls later, after every rank has passed the
+    barrier of the call in between, which it enqueues behind its reads of this buffer."""
+
+    def __init__(self, world: int, rank: int, numel: int, dtype, device, group=None, depth: int = 2):
+        lib = _lib.load()
+        self.world, self.rank, self.group, self.depth, self.calls = world, rank, group, depth, 0
+        self.numel, self.dtype, self.device = numel, dtype, device
+        nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+        self.local, handles = [], []
+        with torch.cuda.device(device):
+            for _ in range(depth):
+                p = ct.c_void_p()
+                _lib.check(lib.actk_peer_buffer_alloc(nbytes, ct.byref(p)), "actk_peer_buffer_alloc")
+                h = ct.create_string_buffer(64)
+                _lib.check(lib.actk_peer_buffer_export(p, h), "actk_peer_buffer_export")
+                self.local.append(p.value)
+                handles.append(h.raw)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, handles, group=group)
+            self._opened = []
+            self.ptrs = [[0] * world for _ in range(depth)]
+            for r, hs in enumerate(everyone):
+                for d in range(depth):
+                    if r == rank:
+                        self.ptrs[d][r] = self.local[d]
+                    else:
+                        p = ct.c_void_p()
+                        _lib.check(lib.actk_peer_buffer_open(hs[d], ct.byref(p)), "actk_peer_buffer_open")
+                        self._opened.append(p.value)
+                        self.ptrs[d][r] = p.value
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def next(self):
+        d = self.calls % self.depth
+        self.calls += 1
+        return self.ptrs[d], self.local[d]
+
+    def fence(self):
+        dist.all_reduce(self._flag, group=self.group)    # stream-ordered: no host synchronisation
+
+    def close(self):
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.actk_peer_buffer_close(ct.c_void_p(p))
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for p in self.local:
+                lib.actk_peer_buffer_free(ct.c_void_p(p))
+        self._opened, self.local = [], []
+
+
 class ShardedSS2DCondV10(torch.nn.Module):
     """Wraps a (replicated) SS2D_cond_v10.  forward takes the same arguments as the layer.
     batch mode: each rank passes ITS rows of B' (the caller shards the batch) and gets its rows back.
     channel mode: every rank passes the same full inputs and gets the full output."""
 
-    def __init__(self, layer: SS2D_cond_v10, mode: str = "channel", group=None):
+    def __init__(self, layer: SS2D_cond_v10, mode: str = "channel", group=None, gather: str = "nccl"):
+        """gather="nccl": one NCCL all-gather of the merged slices (the exchange BASELINE.json names).
+        gather="p2p": the merge kernel itself stores every slice into all ranks' gather buffers over NVLink peer
+        memory (fused compute + collective), followed by a 4-byte barrier all-reduce."""
         super().__init__()
-        self.layer, self.mode, self.group = layer, mode, group
+        if gather not in ("nccl", "p2p"):
+            raise ValueError("gather must be 'nccl' or 'p2p'")
+        self.layer, self.mode, self.group, self.gather = layer, mode, group, gather
+        self._peer = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.plan = ShardPlan("channel", self.world, layer.d_inner, 8) if mode == "channel" else None
@@ -91,20 +161,38 @@ class ShardedSS2DCondV10(torch.nn.Module):
             return layer(x, id_emb, conds, masks)
         lo, hi = self.plan.bounds(self.rank)
         xz1, xz2, tail1, tail2, m1, m2 = layer.project_inputs(x, id_emb, conds, masks)
-        merged = layer.scan_core(xz1, xz2, tail1, tail2, m1, m2, ch_slice=(lo, hi))      # (B', L, Ds)
-        with _timed("all_gather", x.device):
-            gathered = all_gather_slices(merged, self.group)                               # (P, B', L, Ds)
-        y = self.gathered_layernorm(gathered)
+        if self.gather == "p2p":
+            Bp, L, Ds = xz1.shape[0], xz1.shape[1], hi - lo
+            numel = self.world * Bp * L * Ds
+            if self._peer is None or self._peer.numel != numel or self._peer.dtype != xz1.dtype:
+                if self._peer is not None:
+                    self._peer.close()
+                self._peer = PeerGatherBuffers(self.world, self.rank, numel, xz1.dtype, x.device, self.group)
+            ptrs, mine = self._peer.next()
+            layer.scan_core(xz1, xz2, tail1, tail2, m1, m2, ch_slice=(lo, hi), push=(ptrs, self.rank))
+            with _timed("all_gather", x.device):
+                self._peer.fence()
+            y = self.gathered_layernorm(mine, (self.world, Bp, L, Ds), xz1.dtype, x.device)
+            return layer.out_proj(y)
+        else:
+            merged = layer.scan_core(xz1, xz2, tail1, tail2, m1, m2, ch_slice=(lo, hi))  # (B', L, Ds)
+            with _timed("all_gather", x.device):
+                gathered = all_gather_slices(merged, self.group)                           # (P, B', L, Ds)
+        y = self.gathered_layernorm(gathered.data_ptr(), tuple(gathered.shape), gathered.dtype, gathered.device)
+        del gathered
         return layer.out_proj(y)
 
-    def gathered_layernorm(self, gathered: torch.Tensor) -> torch.Tensor:
+    def gathered_layernorm(self, gathered_ptr: int, shape, dtype, device) -> torch.Tensor:
+        """LayerNorm over the gathered (rank, row, slice) layout at `gathered_ptr` (a torch tensor's storage or a
+        peer gather buffer)."""
         lib = _lib.load()
-        P, Bp, L, Ds = gathered.shape
+        P, Bp, L, Ds = shape
         norm = self.layer.out_norm
-        out = torch.empty((Bp, L, P * Ds), dtype=gathered.dtype, device=gathered.device)
-        gamma, beta = norm.weight.to(gathered.dtype), norm.bias.to(gathered.dtype)
-        with torch.cuda.device(gathered.device), _timed("gathered_ln", gathered.device):
-            _lib.check(lib.actk_gathered_layernorm_fwd(_ptr(gathered), P, Bp * L, Ds, _ptr(gamma), _ptr(beta),
-                                                       float(norm.eps), _ptr(out), _DTYPES[gathered.dtype],
-                                                       _stream(gathered)), "actk_gathered_layernorm_fwd")
+        out = torch.empty((Bp, L, P * Ds), dtype=dtype, device=device)
+        gamma, beta = norm.weight.to(dtype), norm.bias.to(dtype)
+        with torch.cuda.device(device), _timed("gathered_ln", device):
+            _lib.check(lib.actk_gathered_layernorm_fwd(ct.c_void_p(gathered_ptr), P, Bp * L, Ds, _ptr(gamma), _ptr(beta),
+                                                       float(norm.eps), _ptr(out), _DTYPES[dtype],
+                                                       ct.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                       "actk_gathered_layernorm_fwd")
         return out

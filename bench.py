@@ -174,7 +174,7 @@ def run_ours(args, rank, world, local_rank):
     channel = world > 1 and args.shard == "channel"
     if channel:   # strong scaling of one layer call: every rank gets the same inputs, scans a d_inner slice
         from actalker_b200.sharded import ShardedSS2DCondV10
-        inner, layer = layer, ShardedSS2DCondV10(layer, mode="channel")
+        inner, layer = layer, ShardedSS2DCondV10(layer, mode="channel", gather=args.gather)
     else:
         inner = layer
     ones = torch.ones(1, 1, 576, 576, dtype=dtype, device=dev)
@@ -274,8 +274,10 @@ def run_ours(args, rank, world, local_rank):
                                f"directions, all-ones masks, {args.params} parameters",
                    "tokens_per_step_per_gpu": Bp * L, "l2": f"inputs rotate over {nrot} resident sets; per-step "
                    "working set (~1.5 GB) exceeds the 126 MB L2", "a_kind": {0: "general", 1: "power"}[a_kind],
-                   "parallelism": (f"d_inner channel-sharded x{world}: replicated in_proj/x_proj, sliced scan, one NCCL "
-                                   "all-gather of the merged slices before out_norm/out_proj") if channel else
+                   "parallelism": (f"d_inner channel-sharded x{world}: replicated in_proj/x_proj, sliced scan, " +
+                                   ("one NCCL all-gather of the merged slices" if args.gather == "nccl" else
+                                    "merge kernel pushes the slices into every rank's gather buffer over NVLink peer "
+                                    "memory + 4-byte barrier all-reduce") + " before out_norm/out_proj") if channel else
                                   f"batch-sharded x{world} (each rank its own B'={Bp} frames), no collective"},
         "roofline": {"bound": "hbm", "kernel": "masked_scan_kernel (actk_masked_scan_fwd)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -321,6 +323,8 @@ def main():
     ap.add_argument("--shard", default="batch", choices=["batch", "channel"],
                     help="N>1: batch = weak scaling, no collective (default); channel = strong scaling of one call "
                          "with the NCCL all-gather before out_norm")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
+                    help="--shard channel: NCCL all-gather (default) or the merge kernel's fused push over NVLink peer memory")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

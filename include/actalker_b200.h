@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 8
+#define ACTK_ABI_VERSION 9
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -182,6 +182,13 @@ typedef struct {
   const void *row_weight[2]; /* NULL, or (L) `dtype`: t_i = round(t_i * row_weight_i[r]) for selected rows — the
                     multiplicative region blend of the older SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797), whose
                     weight is the bicubically downsampled mask itself */
+  /* layernorm == 0 only — fused push all-gather over NVLink peer memory (multi-GPU channel sharding): with
+   * n_peers > 0 the merged slice of row r is stored to peer_out[p] + ((size_t)my_part * Bp*L + r) * D for every
+   * p < n_peers (the (parts, rows, D) layout actk_gathered_layernorm_fwd reads; peer_out[p] is rank p's gather
+   * buffer mapped into this process, own rank included) and `out` is not written.  The caller orders the readers
+   * behind all writers (a stream-ordered barrier collective). */
+  void *peer_out[8];
+  int n_peers, my_part;
 } actk_merge_ln_args;
 
 int actk_merge_layernorm_fwd(const actk_merge_ln_args *args, void *stream);
@@ -207,6 +214,15 @@ int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int D
  *     (the Python layer caches the answer per parameter version).
  * ------------------------------------------------------------------------------------------- */
 int actk_a_structure(const float *A, int dim, int dstate, float rel_tol, int *flag_dev, void *stream);
+
+/* Gather buffers for the fused push all-gather of (3) (peer_out[]): cudaMalloc'ed on the current device, exported
+ * as a 64-byte CUDA IPC handle, opened by the other ranks' processes (mapped with peer access into the opener's
+ * current device).  The host side exchanges the 64-byte handles between the ranks' processes. */
+int actk_peer_buffer_alloc(long long bytes, void **ptr);
+int actk_peer_buffer_free(void *ptr);
+int actk_peer_buffer_export(void *ptr, unsigned char *handle64);
+int actk_peer_buffer_open(const unsigned char *handle64, void **ptr);
+int actk_peer_buffer_close(void *ptr);
 
 /* Bytes of HBM the two scan entry points must move for given sizes (the "algorithmic bytes"
  * Q of BASELINE.md §3 / SURVEY.md §8d); host-only helper used by bench.py and tests. */
