@@ -178,13 +178,16 @@ class ShardedSS2DCondV10(torch.nn.Module):
             merged = layer.scan_core(xz1, xz2, tail1, tail2, m1, m2, ch_slice=(lo, hi))  # (B', L, Ds)
             with _timed("all_gather", x.device):
                 gathered = all_gather_slices(merged, self.group)                           # (P, B', L, Ds)
-        y = self.gathered_layernorm(gathered.data_ptr(), tuple(gathered.shape), gathered.dtype, gathered.device)
-        del gathered
-        return layer.out_proj(y)
+        return layer.out_proj(self.gathered_layernorm(gathered))
 
-    def gathered_layernorm(self, gathered_ptr: int, shape, dtype, device) -> torch.Tensor:
-        """LayerNorm over the gathered (rank, row, slice) layout at `gathered_ptr` (a torch tensor's storage or a
-        peer gather buffer)."""
+    def gathered_layernorm(self, gathered, shape=None, dtype=None, device=None) -> torch.Tensor:
+        """LayerNorm over the gathered (rank, row, slice) layout: `gathered` is a (P, B', L, Ds) tensor, or the raw
+        device address of a peer gather buffer together with shape / dtype / device."""
+        if isinstance(gathered, torch.Tensor):
+            keep, shape, dtype, device = gathered, tuple(gathered.shape), gathered.dtype, gathered.device
+            gathered_ptr = keep.data_ptr()
+        else:
+            gathered_ptr = int(gathered)
         lib = _lib.load()
         P, Bp, L, Ds = shape
         norm = self.layer.out_norm

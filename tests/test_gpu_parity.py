@@ -7,6 +7,7 @@ Tolerances (stated per dtype):
   fp16 I/O : rtol 2e-3, atol 2e-3.
 Index lists and everything integer are compared with torch.equal.
 """
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -499,3 +500,67 @@ def test_fused_ln_out_proj_equals_unfused_route(dtype, cfg):
     err = (got.float() - want.float()).abs()
     assert (err <= step * (1.0 + want.float().abs())).all(), err.max()
     assert (got == want).float().mean() > 0.9
+
+
+def _random_case(i):
+    """Seeded random layer configuration: size, batch, dtype, token-aligned rectangle masks (possibly empty or full) and
+    a forced launch shape.  Rectangles are aligned to the 8-pixel token grid, where the bicubic downsample is exactly
+    0 / 1 on every device, so the index lists of the CPU oracle and the GPU layer cannot differ by rounding."""
+    rng = np.random.RandomState(1000 + i)
+    d_model = int(rng.choice([32, 64, 96, 160, 320]))
+    side = int(rng.randint(3, 21))
+    Bp = int(rng.randint(1, 4))
+    dtype = [torch.float32, torch.bfloat16, torch.float16][i % 3]
+    masks = []
+    for _ in range(2):
+        kind = rng.randint(0, 5)
+        m = torch.zeros(1, 1, side * 8, side * 8)
+        if kind == 0:
+            m[:] = 1
+        elif kind == 1:
+            pass                                           # nothing selected: the branch is the in_proj pass-through
+        else:
+            r0, c0 = rng.randint(0, side), rng.randint(0, side)
+            r1, c1 = rng.randint(r0 + 1, side + 1), rng.randint(c0 + 1, side + 1)
+            m[:, :, 8 * r0:8 * r1, 8 * c0:8 * c1] = 1
+        masks.append(m)
+    shape = [(None, None), (1, 0), (1, 2), (1, 3), (2, 0), (3, 0)][rng.randint(0, 6)]
+    return d_model, side, Bp, dtype, masks, shape
+
+
+@pytest.mark.parametrize("i", range(36))
+def test_layer_random_sweep_matches_oracle(i):
+    """Randomised end-to-end parity of the drop-in layer against the CPU oracle over sizes, batches, dtypes, mask
+    geometries (including empty selections and single-row rectangles) and all three launch shapes of the scan."""
+    from actalker_b200 import SS2D_cond_v10, mamba_layer as ml
+    d_model, side, Bp, dtype, masks, (seg, chain) = _random_case(i)
+    torch.manual_seed(5000 + i)
+    kw = dict(d_model=d_model, d_cond=48, cond_size=32, dropout=0.1, d_state=16, size=side, scan_type="sweep",
+              num_direction=2)
+    ref = SS2D_cond_v10_ref(**kw).eval()
+    with torch.no_grad():
+        ref.exp_unit.A_logs.add_(0.4 * torch.randn_like(ref.exp_unit.A_logs))
+        ref.audio_unit.Ds.copy_(1.0 + 0.3 * torch.randn_like(ref.audio_unit.Ds))
+        ref.out_norm.weight.add_(0.1 * torch.randn_like(ref.out_norm.weight))
+    ours = SS2D_cond_v10(**kw).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    if dtype != torch.float32:
+        ref, ours = ref.to(dtype), ours.to(dtype)
+        for m in (ref, ours):
+            for name, p in m.named_parameters():
+                if any(s in name for s in ("A_logs", "Ds", "dt_projs_bias")):
+                    p.data = p.data.float()
+    ours = ours.cuda()
+    L = side * side
+    x = torch.randn(Bp, L, d_model).to(dtype)
+    id_emb = torch.randn(Bp, 1, 48).to(dtype)
+    conds = torch.randn(Bp, 33, 48).to(dtype)
+    masks = [m.to(dtype) for m in masks]
+    try:
+        ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = seg, chain
+        with torch.no_grad():
+            want = ref(x.clone(), id_emb, conds, masks)
+            got = ours(x.cuda(), id_emb.cuda(), conds.cuda(), [m.cuda() for m in masks])
+    finally:
+        ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = None, None
+    close(got, want, dtype, tol=LAYER_TOL, what=f"random case {i}: d_model {d_model} side {side} B' {Bp} {dtype} shape {(seg, chain)}")

@@ -114,3 +114,21 @@ def test_channel_sharded_layer_equals_unsharded(dtype, d_model, world):
         got = layer.out_proj(wrap.gathered_layernorm(gathered))
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     assert torch.allclose(got.float(), want.float(), rtol=tol, atol=tol), (got.float() - want.float()).abs().max()
+
+
+@pytest.mark.gpu
+def test_peer_memory_gather_equals_nccl_route_on_two_gpus():
+    """The fused push all-gather (merge kernel storing into every rank's gather buffer over NVLink peer memory) must be
+    bit-identical to the NCCL all-gather route and to the unsharded layer.  Needs two visible GPUs (skipped on the
+    single-GPU test box; tools/check_p2p.py is the same check for torchrun, recorded under profiles/)."""
+    import subprocess
+    import sys as _sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_p2p.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "p2p == nccl: True" in r.stdout
