@@ -68,6 +68,7 @@ class _timed:
 # for the merge kernel + cuBLAS GEMM — one CTA per SM around a 160 KB operand tile cannot keep enough HBM loads in
 # flight while it normalises rows.
 FUSE_LN_OUT_PROJ = os.environ.get("ACTK_FUSE_LN_OUT", "0") == "1"
+BATCH_IN_PROJ = os.environ.get("ACTK_BATCH_IN_PROJ", "1") != "0"   # one batched GEMM for in_proj1 / in_proj2
 _SIDE_STREAMS = {}
 SIDE_STREAM = os.environ.get("ACTK_SIDE_STREAM", "1") != "0"
 
@@ -480,10 +481,27 @@ class SS2D_cond_v10(nn.Module):
                 id_tok = self.act2(self.id_proj(id_emb))
                 tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
             tail1, tail2 = tail1.contiguous(), tail2.contiguous()
-        xz1 = self.in_proj1(x)                       # the latent tokens: current stream
-        xz2 = self.in_proj2(x)
+        xz1, xz2 = self._in_proj_both(x)             # the latent tokens: current stream
         fork.join(tail1, tail2)
-        return xz1.contiguous(), xz2.contiguous(), tail1, tail2, m1, m2
+        return xz1, xz2, tail1, tail2, m1, m2
+
+    def _in_proj_both(self, x):
+        """in_proj1(x), in_proj2(x) (mamba_layer.py:1960-1961) as ONE batched GEMM: x enters as a stride-0 batch of two,
+        the weights as a (2, d_model, D) stack, and the two results come out as separate contiguous tensors — x is
+        read once per call instead of once per branch (cuBLAS, config 2: 110 us against 140 us for the two calls)."""
+        w1, w2 = self.in_proj1.weight, self.in_proj2.weight
+        if (not BATCH_IN_PROJ or self.in_proj1.bias is not None or self.in_proj2.bias is not None or w1.dtype != x.dtype
+                or w2.dtype != x.dtype):
+            return self.in_proj1(x).contiguous(), self.in_proj2(x).contiguous()
+        key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.dtype, str(w1.device))
+        if getattr(self, "_w_in_key", None) != key:
+            with torch.no_grad():
+                self._w_in = torch.stack([w1.t(), w2.t()], dim=0).contiguous()      # (2, d_model, D)
+            self._w_in_key = key
+        Bp, L, dm = x.shape
+        x2 = x.reshape(1, Bp * L, dm).expand(2, Bp * L, dm)
+        xz = torch.bmm(x2, self._w_in)                                               # (2, B'L, D)
+        return xz[0].view(Bp, L, -1), xz[1].view(Bp, L, -1)
 
     def _check_forward_only(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):

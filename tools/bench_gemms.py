@@ -34,3 +34,9 @@ print("dt_proj (lda=xw view)    %.1f us" % t(lambda: torch.mm(xd[:, 64:], Wdt)))
 print("out_proj                 %.1f us" % t(lambda: torch.nn.functional.linear(y, Wo)))
 Wbd = torch.zeros(2 * xw, 2 * D, device=dev, dtype=dt); Wbd[:xw, :D] = Wx; Wbd[xw:, D:] = Wx
 print("x_proj both (blockdiag)  %.1f us" % t(lambda: torch.mm(xz, Wbd.t())))
+Wb = torch.stack([W1.t().contiguous(), W2.t().contiguous()], 0)          # (2, K, N)
+xe = x.unsqueeze(0).expand(2, M, dm)
+print("in_proj bmm, expanded x  %.1f us" % t(lambda: torch.bmm(xe, Wb)))
+outb = torch.empty(2, M, D, device=dev, dtype=dt)
+print("in_proj bmm out=         %.1f us" % t(lambda: torch.bmm(xe, Wb, out=outb)))
+print("in_proj matmul broadcast %.1f us" % t(lambda: torch.matmul(x.unsqueeze(0), Wb)))
