@@ -17,7 +17,14 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libactalker_b200.so")
-SOURCES = ["api.cu", "masked_scan.cu", "selective_scan.cu", "merge_ln.cu", "ln_outproj.cu"]
+# (source, extra defines, object tag).  selective_scan.cu and merge_ln.cu are compiled once per I/O dtype
+# (-DACTK_TU_DTYPE=n instantiates that dtype's kernels only) plus once for their C-ABI entry points, and the masked
+# scan has one translation unit per dt-rank slab count, so that the long template instantiations build in parallel.
+SOURCES = [("api.cu", (), ""), ("masked_scan.cu", (), ""),
+           ("masked_scan_ks0.cu", (), ""), ("masked_scan_ks2.cu", (), ""), ("masked_scan_ks3.cu", (), ""),
+           ("masked_scan_ks5.cu", (), ""), ("ln_outproj.cu", (), ""),
+           ("selective_scan.cu", (), ""), ("merge_ln.cu", (), "")] + \
+          [(src, (f"ACTK_TU_DTYPE={n}",), f"_t{n}") for src in ("selective_scan.cu", "merge_ln.cu") for n in (0, 1, 2)]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--use_fast_math", "-Xcompiler", "-fPIC",
@@ -53,9 +60,9 @@ def build(force: bool = False, verbose: bool = False, out: str = None, defs=()) 
     log = []
     tag = os.path.splitext(os.path.basename(out))[0]
     procs = []
-    for src in SOURCES:   # one nvcc per translation unit, all at once
-        obj = os.path.join(LIB_DIR, (tag + "_" if variant else "") + src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-c", os.path.join(CSRC, src), "-o", obj]
+    for src, src_defs, otag in SOURCES:   # one nvcc per translation unit, all at once
+        obj = os.path.join(LIB_DIR, (tag + "_" if variant else "") + src.replace(".cu", otag + ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in (*defs, *src_defs)], "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)
     for src, pr in procs:

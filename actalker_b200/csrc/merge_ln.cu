@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) gathered_ln_kernel(const T *__restrict__ 
 }
 
 template <typename T>
-static int launch_gathered(const void *in, const void *gamma, const void *beta, void *out, int parts, long long rows,
+int launch_gathered(const void *in, const void *gamma, const void *beta, void *out, int parts, long long rows,
                            int Ds, float eps, cudaStream_t stream) {
   const int vpl = ((parts * Ds >> 3) + 31) / 32;
   const unsigned grid = (unsigned)((rows + 3) / 4);
@@ -236,7 +236,7 @@ static int launch_gathered(const void *in, const void *gamma, const void *beta, 
 }
 
 template <typename T>
-static int launch_merge(const actk_merge_ln_args *a, cudaStream_t stream) {
+int launch_merge(const actk_merge_ln_args *a, cudaStream_t stream) {
   MergeParams P;
   P.a = *a;
   const int vpl = ((a->D >> 3) + 31) / 32;
@@ -250,8 +250,28 @@ static int launch_merge(const actk_merge_ln_args *a, cudaStream_t stream) {
   return ACTK_OK;
 }
 
+// Compiled once per I/O dtype with -DACTK_TU_DTYPE=0/1/2 (kernel instantiations) and once without it (C-ABI entries).
+#define ACTK_LN_INST(KW, T)                                                                                              \
+  KW template int launch_gathered<T>(const void *, const void *, const void *, void *, int, long long, int, float, cudaStream_t); \
+  KW template int launch_merge<T>(const actk_merge_ln_args *, cudaStream_t);
+#if defined(ACTK_TU_DTYPE)
+#if ACTK_TU_DTYPE == 0
+ACTK_LN_INST(, float)
+#elif ACTK_TU_DTYPE == 1
+ACTK_LN_INST(, __half)
+#else
+ACTK_LN_INST(, __nv_bfloat16)
+#endif
+#else
+ACTK_LN_INST(extern, float)
+ACTK_LN_INST(extern, __half)
+ACTK_LN_INST(extern, __nv_bfloat16)
+#endif
+#undef ACTK_LN_INST
+
 }  // namespace actk
 
+#ifndef ACTK_TU_DTYPE
 using namespace actk;
 
 extern "C" int actk_merge_layernorm_fwd(const actk_merge_ln_args *a, void *stream) {
@@ -299,3 +319,4 @@ extern "C" int actk_gathered_layernorm_fwd(const void *in, int parts, long long 
     default: return launch_gathered<__nv_bfloat16>(in, gamma, beta, out, parts, rows, Ds, eps, st);
   }
 }
+#endif  // !ACTK_TU_DTYPE

@@ -169,7 +169,7 @@ __global__ void selective_scan_generic_kernel(const __grid_constant__ actk_scan_
 }
 
 template <typename T>
-static int launch_op(const actk_scan_args *a, cudaStream_t stream) {
+int launch_op(const actk_scan_args *a, cudaStream_t stream) {
   if (a->dstate != kN) {
     dim3 grid((a->dim + 63) / 64, a->batch);
     selective_scan_generic_kernel<T><<<grid, 64, 0, stream>>>(*a);
@@ -195,8 +195,25 @@ static int launch_op(const actk_scan_args *a, cudaStream_t stream) {
   return ACTK_OK;
 }
 
+// This file is compiled four times (build.py): once per I/O dtype with -DACTK_TU_DTYPE=0/1/2, which instantiates the
+// kernels of that dtype only, and once without it for the C-ABI entry — the instantiations build in parallel.
+#if defined(ACTK_TU_DTYPE)
+#if ACTK_TU_DTYPE == 0
+template int launch_op<float>(const actk_scan_args *, cudaStream_t);
+#elif ACTK_TU_DTYPE == 1
+template int launch_op<__half>(const actk_scan_args *, cudaStream_t);
+#else
+template int launch_op<__nv_bfloat16>(const actk_scan_args *, cudaStream_t);
+#endif
+#else
+extern template int launch_op<float>(const actk_scan_args *, cudaStream_t);
+extern template int launch_op<__half>(const actk_scan_args *, cudaStream_t);
+extern template int launch_op<__nv_bfloat16>(const actk_scan_args *, cudaStream_t);
+#endif
+
 }  // namespace actk
 
+#ifndef ACTK_TU_DTYPE
 using namespace actk;
 
 extern "C" int actk_selective_scan_fwd(const actk_scan_args *a, void *stream) {
@@ -220,3 +237,4 @@ extern "C" int actk_selective_scan_fwd(const actk_scan_args *a, void *stream) {
     default: return launch_op<__nv_bfloat16>(a, st);
   }
 }
+#endif  // !ACTK_TU_DTYPE
