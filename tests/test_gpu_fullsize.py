@@ -2,6 +2,8 @@
 take minutes: size-independent properties of the path, plus a full-size cross-check of the fused layer kernels
 against the reference's own op graph (oracle layer code on the GPU) driven by the operator-contract kernel —
 two different kernels, layouts and code paths that must agree."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -153,3 +155,33 @@ def test_operator_linearity_in_u_full_size():
     lhs, rhs = f(u1 + 2 * u2), f(u1) + 2 * f(u2)
     scale = rhs.abs().max()
     assert ((lhs - rhs).abs() <= 1e-4 * scale + 1e-4 * rhs.abs()).all()
+
+
+def test_bench_line_carries_the_contract_keys():
+    """bench.py prints ONE JSON line with the driver's contract: metric / value / unit / timing fields, the roofline of the
+    dominant kernel measured live, the end-to-end number through the public host-buffer API with its byte counts,
+    clocks sampled during the timed region and the count of this repo's kernel launches."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "masked selective-scan Gtokens/s" and d["unit"] == "Gtokens/s" and d["n_gpus"] == 1
+    assert d["steps"] == 3 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0.05 < rf["frac"] < 1.0
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert abs(rf["achieved"] - rf["algorithmic_bytes"] / (rf["kernel_ms"] * 1e-3) / 1e9) < 1e-3 * rf["achieved"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
+    assert d["gpu_launches"] == 2 * d["steps"]
+    assert abs(d["value"] - 25 * 5184 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6
