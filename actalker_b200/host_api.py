@@ -66,7 +66,9 @@ class HostStreamedLayer:
         self.d2h.wait_event(s["computed"])
         with torch.cuda.stream(self.d2h):
             out.copy_(s["y"], non_blocking=True)
-            s["y"].record_stream(self.d2h)
+            # no record_stream on y: it stays referenced by the slot until submit(i + depth) replaces it, and that
+            # call's compute waits for `downloaded` first — so the block cannot be reused while this copy reads it
+            # (record_stream would push the allocator into deferred frees and occasional cudaMalloc stalls)
             s["downloaded"].record(self.d2h)
 
     def drain(self):
