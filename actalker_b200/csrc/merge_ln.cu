@@ -63,8 +63,13 @@ __device__ __forceinline__ void store8(T *p, const float (&v)[8]) {
   }
 }
 
+// 6 CTAs per SM (<= 80 registers) for the common VPL = 4: one register more costs a whole CTA of loads in flight
+// (measured: 81 registers -> 5 CTAs -> 176 us instead of 160 us at config 2).
+#ifndef ACTK_MERGE_MINB
+#define ACTK_MERGE_MINB 6
+#endif
 template <typename T, int VPL>
-__global__ void __launch_bounds__(128) merge_ln_kernel(const __grid_constant__ MergeParams P) {
+__global__ void __launch_bounds__(128, VPL <= 4 ? ACTK_MERGE_MINB : 1) merge_ln_kernel(const __grid_constant__ MergeParams P) {
   const actk_merge_ln_args &a = P.a;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
