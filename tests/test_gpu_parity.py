@@ -564,3 +564,39 @@ def test_layer_random_sweep_matches_oracle(i):
     finally:
         ml.SCAN_SEGMENTS, ml.SCAN_CHAIN = None, None
     close(got, want, dtype, tol=LAYER_TOL, what=f"random case {i}: d_model {d_model} side {side} B' {Bp} {dtype} shape {(seg, chain)}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("use_z", [False, True])
+def test_operator_matches_the_upstream_derived_cuda_kernel_in_vllm(dtype, use_z):
+    """Independent pin of the operator contract: vLLM ships a CUDA selective scan derived from mamba-ssm's own kernel
+    (csrc/mamba/mamba_ssm/selective_scan_fwd.cu, bound as vllm._custom_ops.selective_scan_fwd) — the closest thing to the
+    reference's `selective_scan_fn` (mamba-ssm 1.2.0.post1 is not installable here) that exists on the box.  Same
+    inputs through both kernels: grouped B/C, D skip, delta bias, softplus, optional SiLU(z) gate, last state."""
+    try:
+        from vllm.model_executor.layers.mamba.ops.mamba_ssm import selective_scan_fn as vllm_scan
+    except Exception as e:   # noqa: BLE001
+        pytest.skip(f"vllm's mamba kernel is not importable here: {type(e).__name__}")
+    from actalker_b200 import selective_scan_fn
+    torch.manual_seed(11)
+    batch, dim, L, N = 3, 256, 517, 16
+    dev = "cuda"
+    u = torch.randn(batch, dim, L, device=dev).to(dtype)
+    delta = (0.5 * torch.randn(batch, dim, L, device=dev)).to(dtype)
+    A = -torch.exp(torch.randn(dim, N, device=dev) * 0.5)
+    Bm = torch.randn(batch, 1, N, L, device=dev).to(dtype)
+    Cm = torch.randn(batch, 1, N, L, device=dev).to(dtype)
+    D = torch.randn(dim, device=dev)
+    bias = torch.randn(dim, device=dev) - 2.0
+    z = torch.randn(batch, dim, L, device=dev).to(dtype) if use_z else None
+    ours, last = selective_scan_fn(u, delta, A, Bm, Cm, D, z, bias, True, return_last_state=True)
+    state = torch.zeros(batch, dim, N, device=dev, dtype=dtype)
+    try:
+        theirs = vllm_scan(u.clone(), state, delta.clone(), A, Bm.clone(), Cm.clone(), D, None if z is None else z.clone(),
+                           bias, True, has_initial_state=torch.zeros(batch, dtype=torch.bool, device=dev))
+    except Exception as e:   # noqa: BLE001 - the op may be compiled out of this vllm build
+        pytest.skip(f"vllm selective_scan_fwd not runnable here: {type(e).__name__}: {str(e)[:120]}")
+    close(ours, theirs, dtype, what="vs vllm mamba kernel")
+    rt, at = TOL[dtype]
+    assert torch.allclose(last.float(), state.float(), rtol=max(rt, 2e-3), atol=max(at, 2e-3)), \
+        (last.float() - state.float()).abs().max()
