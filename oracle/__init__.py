@@ -12,7 +12,9 @@ Pin status:
     vendored under /root/reference and not installable here.  The restatement
     follows the package's published semantics and is
     cross-checked against the independent statement of the same recurrence in
-    transformers' `MambaMixer.slow_forward` (tests/test_oracle.py).
+    transformers' `MambaMixer.slow_forward` (tests/test_oracle.py) and, on the GPU
+    box, the CUDA path is compared with the mamba-ssm-derived selective-scan
+    kernel that ships in vLLM (tests/test_gpu_parity.py, test_gpu_fullsize.py).
   * mask level (`downsample`): restated from diffusers==0.29.2
     (requirements.txt:10), also absent; pinned by known-answer cases.
   * layer level (`SS2D_cond_v10_ref`, `SS2D_Unit_ref`): PINNED — the real

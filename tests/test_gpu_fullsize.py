@@ -185,3 +185,52 @@ def test_bench_line_carries_the_contract_keys():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
     assert d["gpu_launches"] == 2 * d["steps"]
     assert abs(d["value"] - 25 * 5184 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6
+
+
+def test_reference_op_graph_on_the_upstream_derived_kernel_full_size(capsys):
+    """The reference's own op graph (oracle layer code, op for op: scatter passes, flipped copies, einsums) on the GPU,
+    driven by the mamba-ssm-derived CUDA kernel that ships in vLLM — the nearest runnable stand-in for
+    `SS2D_cond_v10` + mamba-ssm on this box — against the drop-in layer at BASELINE config 2.  Checks parity and that
+    the drop-in is faster; the measured ratio is printed (pytest -s) and recorded in DESIGN.md."""
+    try:
+        from vllm.model_executor.layers.mamba.ops.mamba_ssm import selective_scan_fn as vllm_scan
+    except Exception as e:   # noqa: BLE001
+        pytest.skip(f"vllm's mamba kernel is not importable here: {type(e).__name__}")
+    dtype = torch.bfloat16
+
+    def upstream_scan(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+        state = torch.zeros(u.shape[0], u.shape[1], A.shape[1], device=u.device, dtype=u.dtype)
+        flag = torch.zeros(u.shape[0], dtype=torch.bool, device=u.device)
+        return vllm_scan(u.contiguous(), state, delta.contiguous().clone(), A, Bm.contiguous(), Cm.contiguous(), D, z,
+                         delta_bias, delta_softplus, has_initial_state=flag)
+
+    ours = make_layer(dtype)
+    ref = SS2D_cond_v10_ref(d_model=DM, d_cond=1024, cond_size=32, dropout=0.1, d_state=16, size=SIDE,
+                            scan_type="sweep", num_direction=2).eval().to(dtype).cuda()
+    for n, p in ref.named_parameters():
+        p.data = dict(ours.named_parameters())[n].data.clone()
+    x, idm, cd = inputs(dtype)
+    m = masks("ones", dtype)
+    with torch.no_grad():
+        try:
+            want = ref(x.clone(), idm, cd, m, selective_scan=upstream_scan)
+        except Exception as e:   # noqa: BLE001
+            pytest.skip(f"vllm selective_scan_fwd not runnable here: {type(e).__name__}: {str(e)[:120]}")
+        got = ours(x, idm, cd, m)
+        err = (got.float() - want.float()).abs()
+        assert (err <= 3e-2 + 3e-2 * want.float().abs()).all(), err.max()
+
+        def t(fn, n=5):
+            fn(); torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(n):
+                fn()
+            e.record(); torch.cuda.synchronize()
+            return s.elapsed_time(e) / n
+        t_ref = t(lambda: ref(x.clone(), idm, cd, m, selective_scan=upstream_scan))
+        t_ours = t(lambda: ours(x, idm, cd, m))
+    with capsys.disabled():
+        print(f"\n[config 2, bf16] reference op graph + mamba-ssm-derived kernel: {t_ref:.2f} ms/layer; drop-in: {t_ours:.2f} ms "
+              f"({t_ref / t_ours:.1f}x)")
+    assert t_ours < t_ref
