@@ -291,6 +291,9 @@ def run_ours(args, rank, world, local_rank):
                          "smsp_cycles_per_warp_step": {0: 154.0, 1: 117.0}[a_kind],
                          "ms": (updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3,
                          "frac_of_floor": ((updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3) / scan_ms,
+                         # the roofline fraction this kernel would show if it ran exactly at that floor: what
+                         # fp32 per-(channel, state) exponentials allow on 148 SMs, whatever the memory system does
+                         "frac_at_floor": (q / peak / 1e9) / ((updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9),
                          "source": "profiles/r01_microbench.txt (B200 at 1965 MHz)"},
                      **{k + "_ms": v for k, v in extra.items()}},
         "e2e": {"value": tokens / (ms_e2e * 1e-3) / 1e9, "unit": "Gtokens/s",
