@@ -168,7 +168,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
       P.chain_ctr = P.chain_flag + P.nq;
       ACTK_CUDA_OK(cudaMemsetAsync(P.chain_flag, 0, ((size_t)P.nq + 1) * sizeof(int), stream));
       const unsigned nblocks = (unsigned)P.nq * a->chain_chunks;
-      launch_any<T>(ks, pw, 2, dim3(nblocks), stream, P, M);
+      launch_any<T>(ks, pw, 2 | (P.nq > 7 * 148 ? 8 : 0), dim3(nblocks), stream, P, M);
       ACTK_CUDA_OK(cudaGetLastError());
       i = j;
       continue;
@@ -183,7 +183,8 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
                                                                           a->D, nseg);
       ACTK_CUDA_OK(cudaGetLastError());
     }
-    launch_any<T>(ks, pw, 0, grid, stream, P, M);
+    // single level: more sequence-CTAs than 7 per SM can hold -> the 3-slot ring's 8th CTA per SM pays
+    launch_any<T>(ks, pw, (nseg == 1 && (long long)grid.x * grid.y * grid.z > 7 * 148) ? 8 : 0, grid, stream, P, M);
     ACTK_CUDA_OK(cudaGetLastError());
     i = j;
   }

@@ -133,10 +133,14 @@ struct TileGeo {
 // scans, and publishes (release).  Chunks of one sequence land on different SMs, so every sequence advances at the
 // average rate and fast SMs simply take more items.  A waiting CTA only ever waits for a CTA that drew a smaller
 // ticket, i.e. one that is already running: no deadlock whatever the hardware's dispatch order.
-template <typename T, bool POWER_A, int MODE, int KS>
+// SHORT_RING: a 3-slot ring for 16-bit I/O (23.6 KB of shared memory, 8 CTAs per SM instead of 7) — the host picks it
+// when a launch has more sequences than 7 CTAs per SM can hold (CFG x2 / x4, the UNet's d_model 640 / 1280 layers):
+// measured on B200, config-2 shape at B' = 50 / 100: 2.96 -> 2.90 ms, 5.88 -> 5.76 ms; at B' = 25 (1000 sequences, all
+// resident either way) the 4-slot ring is 3.5 % faster and stays.
+template <typename T, bool POWER_A, int MODE, int KS, bool SHORT_RING = false>
 __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant__ MaskedParams<T> P,
                                                           const __grid_constant__ MaskedMaps M) {
-  constexpr int S = ring_stages<T, KS>();
+  constexpr int S = SHORT_RING ? 3 : ring_stages<T, KS>();
   constexpr bool k16 = sizeof(T) == 2;
   constexpr bool kFused = KS > 0;
   // the single-thread TMA work (tile loads, y stores) runs in warp 1 when warp 0 issues the MMAs: both are serial
@@ -591,9 +595,24 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   if (tid == kTmaTid) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
 }
 
-// One kernel launch for a given (T, KS); MODE and POWER_A are runtime here.
+// One kernel launch for a given (T, KS); MODE and POWER_A are runtime here.  mode | 8 asks for the 3-slot ring
+// (16-bit I/O without the fused dt_proj, single-level and chained launches).
 template <typename T, int KS>
 void launch_ks(bool pw, int mode, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P, const MaskedMaps &M) {
+  const bool short_ring = (mode & 8) != 0;
+  mode &= 7;
+  if constexpr (sizeof(T) == 2 && KS == 0) {
+    if (short_ring && mode == 2) {
+      if (pw) masked_scan_kernel<T, true, 2, KS, true><<<grid, kCh, 0, stream>>>(P, M);
+      else masked_scan_kernel<T, false, 2, KS, true><<<grid, kCh, 0, stream>>>(P, M);
+      return;
+    }
+    if (short_ring && mode == 0) {
+      if (pw) masked_scan_kernel<T, true, 0, KS, true><<<grid, kCh, 0, stream>>>(P, M);
+      else masked_scan_kernel<T, false, 0, KS, true><<<grid, kCh, 0, stream>>>(P, M);
+      return;
+    }
+  }
   if (mode == 2) {
     if (pw) masked_scan_kernel<T, true, 2, KS><<<grid, kCh, 0, stream>>>(P, M);
     else masked_scan_kernel<T, false, 2, KS><<<grid, kCh, 0, stream>>>(P, M);
