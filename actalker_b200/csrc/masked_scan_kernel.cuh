@@ -102,11 +102,13 @@ __device__ __forceinline__ void tmem_dealloc32(uint32_t taddr) {
 // thread i of the warp reads 4 (or 1) consecutive 32-bit columns of TMEM lane (lane field of taddr) + i.
 // The load is asynchronous: tmem_ld4_issue starts it, tmem_ld4_wait makes the registers valid (and ties them to the
 // wait through in/out operands so no use can be scheduled ahead of it).
-__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+template <int NR>
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[NR]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld4_wait(uint32_t (&r)[4]) {
+template <int NR>
+__device__ __forceinline__ void tmem_ld4_wait(uint32_t (&r)[NR]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
 }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
@@ -143,6 +145,12 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   constexpr int S = SHORT_RING ? 3 : ring_stages<T, KS>();
   constexpr bool k16 = sizeof(T) == 2;
   constexpr bool kFused = KS > 0;
+  // Steps software-pipelined together.  8 (two groups per tile) for 16-bit launches that leave a free register budget
+  // at 7 CTAs per SM: all prologues (softplus chains) of 8 steps overlap and decay(i+1) runs ahead of apply(i) across
+  // the whole group — measured on B200: config 2 1.508 -> 1.482 ms, a rank's d_inner slice 1.03 -> 0.98 ms (N=2),
+  // 0.70 -> 0.66 ms (N=8), rectangle masks at B'=25 0.418 -> 0.400 ms.  With the 3-slot ring (8 CTAs per SM, CFG x4) 4
+  // is 1 % faster and stays; fp32 I/O and the fused dt_proj (4 TMEM columns per load) keep 4.
+  constexpr int kG = (sizeof(T) == 2 && !kFused && !SHORT_RING) ? 8 : kGroup;
   // the single-thread TMA work (tile loads, y stores) runs in warp 1 when warp 0 issues the MMAs: both are serial
   // instruction chains on the tile's critical path, so they go side by side
   constexpr int kTmaTid = kFused ? 32 : 0;
@@ -465,25 +473,25 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       if (MODE == 1) {
         int r = 0;
         if (g.nrows == kT) {
-          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
-          if constexpr (kFused) { tmem_ld4_issue(tacc + (k ? kT - kGroup : 0), dv); tmem_ld4_wait(dv); }
+          uint32_t dv[kG] = {}, dn[kG] = {};
+          if constexpr (kFused) { tmem_ld4_issue(tacc + (k ? kT - kG : 0), dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
-          for (; r < kT; r += kGroup) {
+          for (; r < kT; r += kG) {
             const int j0 = k ? kT - 1 - r : r, dj = k ? -1 : 1;
             if constexpr (kFused) {   // next group's delta values travel from TMEM while this group is scanned
-              if (r + kGroup < kT) tmem_ld4_issue(tacc + (k ? kT - 2 * kGroup - r : r + kGroup), dn);
+              if (r + kG < kT) tmem_ld4_issue(tacc + (k ? kT - 2 * kG - r : r + kG), dn);
             }
-            sumdt += cs.template run_state<kGroup, true>(
+            sumdt += cs.template run_state<kG, true>(
                 [&](int i) { return IO<T>::ld(us + (j0 + dj * i) * kCh); },
                 [&](int i) {
-                  if constexpr (kFused) return IO<T>::rnd(__uint_as_float(k ? dv[kGroup - 1 - i] : dv[i]));
+                  if constexpr (kFused) return IO<T>::rnd(__uint_as_float(k ? dv[kG - 1 - i] : dv[i]));
                   else return IO<T>::ld(ds + (j0 + dj * i) * kCh);
                 },
                 [&](int i) { return bcs + (j0 + dj * i) * 2 * kN; });
             if constexpr (kFused) {
               tmem_ld4_wait(dn);
 #pragma unroll
-              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+              for (int i = 0; i < kG; ++i) dv[i] = dn[i];
             }
           }
         }
@@ -496,19 +504,19 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
           sumdt += si.dt;
         }
       } else if (g.nrows == kT) {
-        // smem row of step r: r (direction 0) or 15 - r (direction 1); kGroup steps are software-pipelined
+        // smem row of step r: r (direction 0) or 15 - r (direction 1); kG steps are software-pipelined
         if (k == 0) {
-          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
+          uint32_t dv[kG] = {}, dn[kG] = {};
           if constexpr (kFused) { tmem_ld4_issue(tacc, dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
-          for (int r0 = 0; r0 < kT; r0 += kGroup) {
+          for (int r0 = 0; r0 < kT; r0 += kG) {
             const T *u0 = us + r0 * kCh, *dl0 = ds + r0 * kCh;
             const float *b0 = bcs + r0 * 2 * kN;
             T *y0 = ys + r0 * kCh;
             if constexpr (kFused) {   // next group's delta values travel from TMEM while this group is scanned
-              if (r0 + kGroup < kT) tmem_ld4_issue(tacc + r0 + kGroup, dn);
+              if (r0 + kG < kT) tmem_ld4_issue(tacc + r0 + kG, dn);
             }
-            cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 + i * kCh); },
+            cs.template run<kG, true>([&](int i) { return IO<T>::ld(u0 + i * kCh); },
                                           [&](int i) {
                                             if constexpr (kFused) return IO<T>::rnd(__uint_as_float(dv[i]));
                                             else return IO<T>::ld(dl0 + i * kCh);
@@ -518,24 +526,24 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
             if constexpr (kFused) {
               tmem_ld4_wait(dn);
 #pragma unroll
-              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+              for (int i = 0; i < kG; ++i) dv[i] = dn[i];
             }
           }
         } else {
-          uint32_t dv[kGroup] = {}, dn[kGroup] = {};
-          if constexpr (kFused) { tmem_ld4_issue(tacc + kT - kGroup, dv); tmem_ld4_wait(dv); }
+          uint32_t dv[kG] = {}, dn[kG] = {};
+          if constexpr (kFused) { tmem_ld4_issue(tacc + kT - kG, dv); tmem_ld4_wait(dv); }
 #pragma unroll 1
-          for (int r0 = 0; r0 < kT; r0 += kGroup) {
+          for (int r0 = 0; r0 < kT; r0 += kG) {
             const int j0 = kT - 1 - r0;
             const T *u0 = us + j0 * kCh, *dl0 = ds + j0 * kCh;
             const float *b0 = bcs + j0 * 2 * kN;
             T *y0 = ys + j0 * kCh;
             if constexpr (kFused) {
-              if (r0 + kGroup < kT) tmem_ld4_issue(tacc + kT - 2 * kGroup - r0, dn);
+              if (r0 + kG < kT) tmem_ld4_issue(tacc + kT - 2 * kG - r0, dn);
             }
-            cs.template run<kGroup, true>([&](int i) { return IO<T>::ld(u0 - i * kCh); },
+            cs.template run<kG, true>([&](int i) { return IO<T>::ld(u0 - i * kCh); },
                                           [&](int i) {
-                                            if constexpr (kFused) return IO<T>::rnd(__uint_as_float(dv[kGroup - 1 - i]));
+                                            if constexpr (kFused) return IO<T>::rnd(__uint_as_float(dv[kG - 1 - i]));
                                             else return IO<T>::ld(dl0 - i * kCh);
                                           },
                                           [&](int i) { return b0 - i * 2 * kN; },
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
             if constexpr (kFused) {
               tmem_ld4_wait(dn);
 #pragma unroll
-              for (int i = 0; i < kGroup; ++i) dv[i] = dn[i];
+              for (int i = 0; i < kG; ++i) dv[i] = dn[i];
             }
           }
         }

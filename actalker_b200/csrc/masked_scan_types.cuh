@@ -9,7 +9,7 @@ namespace actk {
 
 constexpr int kCh = 64;  // channels per CTA == threads per CTA
 constexpr int kT = 16;   // time steps per tile
-constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::run)
+constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::run); see kG in the kernel
 #ifndef ACTK_STAGES16
 #define ACTK_STAGES16 4
 #endif

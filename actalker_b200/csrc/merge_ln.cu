@@ -69,7 +69,7 @@ __device__ __forceinline__ void store8(T *p, const float (&v)[8]) {
 #define ACTK_MERGE_MINB 6
 #endif
 template <typename T, int VPL>
-__global__ void __launch_bounds__(128, VPL <= 4 ? ACTK_MERGE_MINB : 1) merge_ln_kernel(const __grid_constant__ MergeParams P) {
+__global__ void __launch_bounds__(128, (VPL <= 4 && sizeof(T) == 2) ? ACTK_MERGE_MINB : 1) merge_ln_kernel(const __grid_constant__ MergeParams P) {
   const actk_merge_ln_args &a = P.a;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
