@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   // the whole group — measured on B200: config 2 1.508 -> 1.482 ms, a rank's d_inner slice 1.03 -> 0.98 ms (N=2),
   // 0.70 -> 0.66 ms (N=8), rectangle masks at B'=25 0.418 -> 0.400 ms.  With the 3-slot ring (8 CTAs per SM, CFG x4) 4
   // is 1 % faster and stays; fp32 I/O and the fused dt_proj (4 TMEM columns per load) keep 4.
-  constexpr int kG = (sizeof(T) == 2 && !kFused && !SHORT_RING) ? 8 : kGroup;
+#ifndef ACTK_GROUP_WIDE
+#define ACTK_GROUP_WIDE 8
+#endif
+  constexpr int kG = (sizeof(T) == 2 && !kFused && !SHORT_RING) ? ACTK_GROUP_WIDE : kGroup;
   // the single-thread TMA work (tile loads, y stores) runs in warp 1 when warp 0 issues the MMAs: both are serial
   // instruction chains on the tile's critical path, so they go side by side
   constexpr int kTmaTid = kFused ? 32 : 0;
