@@ -15,7 +15,8 @@ weak scaling.  One JSON line is printed by rank 0.
   e2e       same through the public module call from pinned HOST buffers, H2D of x/id/conds and D2H of y timed
   roofline  the dominant kernel (actk_masked_scan_fwd) alone: algorithmic bytes Q / its mean
             launch duration measured with CUDA events inside the timed region, against MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (restated selective_scan_ref path) on the host cores, BASELINE config 1
+  cpu_baseline  the CPU oracle (restated selective_scan_ref path) on the host cores, a bounded sample (1-2 frames) of
+                the same workload; `--impl reference` times that path alone, as many frames per step as fit the budget
 """
 import argparse
 import json
@@ -116,41 +117,61 @@ def scan_bytes(Bp, L, D, es):
     return q(Bp, L + 33, 2 * D, 2, 16, es) + q(Bp, L + 2, 2 * D, 2, 16, es)
 
 
-def cpu_baseline(frames, threads):
-    """CPU oracle layer on BASELINE config 1 (B'=frames<=14, 32x32 tokens, d_model 320, fp32)."""
+CPU_DTYPES = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}
+
+
+def cpu_baseline(frames, threads, side=72, d_model=320, dtype="bf16"):
+    """The reference's CPU path (oracle port of the layer + selective_scan_ref) on a bounded sample of the bench
+    workload: `frames` of its frames at side x side tokens, same d_model / dtype / branches / masks.  The token loop
+    of selective_scan_ref is sequential Python over L' = side^2 + 33 steps, so a pass takes seconds per frame."""
     from oracle import SS2D_cond_v10_ref
     torch.set_num_threads(threads)
-    layer = make_layer(SS2D_cond_v10_ref, 320, torch.float32, "init", "cpu", SEED + 1)
-    x, idm, cd = host_inputs(frames, 1024, 320, torch.float32, SEED + 1, pin=False)
-    ones = torch.ones(1, 1, 256, 256)
+    dt_ = CPU_DTYPES[dtype]
+    if dt_ == torch.float16:
+        dt_ = torch.bfloat16     # CPU GEMMs in fp16 are not generally available; same width, same traffic
+    layer = make_layer(SS2D_cond_v10_ref, d_model, dt_, "init", "cpu", SEED + 1)
+    x, idm, cd = host_inputs(frames, side * side, d_model, dt_, SEED + 1, pin=False)
+    ones = torch.ones(1, 1, 8 * side, 8 * side, dtype=dt_)
     with torch.no_grad():
         t0 = time.perf_counter()
         layer(x, idm, cd, [ones, ones])
         dt = time.perf_counter() - t0
-    return frames * 1024 / dt / 1e9, dt
+    return frames * side * side / dt / 1e9, dt
+
+
+def workload_name(Bp, frames, cfg, side, d_model, params):
+    return (f"SS2D_cond_v10 layer forward, BASELINE configs[1]: B'={Bp} ({frames} frames x CFG {cfg}) x {side}x{side} "
+            f"tokens, d_model {d_model}, d_state 16, 2 branches x 2 directions, all-ones masks, {params} parameters")
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path (selective_scan_ref inside the restated
+    SS2D_cond_v10; mamba-ssm's CUDA build cannot exist here) on the host cores, on THIS bench's workload, each step a
+    bounded sample of it (as many of its frames as the time budget allows, at least one)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    _, t1 = cpu_baseline(1, threads)                                  # calibration pass (also warms torch)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    frames = max(1, min(14, int(budget / max(t1, 1e-3))))
+    side = int(72 / (args.d_model / 320))
+    Bp = args.frames * args.cfg
+    _, t1 = cpu_baseline(1, threads, side, args.d_model, args.dtype)     # calibration pass (also warms torch)
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    # a pass costs a fixed Python-loop part plus ~0.25 of it per extra frame (measured: 12.0 s / 14.5 s for 1 / 2 frames)
+    frames = max(1, min(Bp, 1 + int((budget - t1) / (0.3 * t1)))) if budget > t1 else 1
     for _ in range(args.warmup):
-        cpu_baseline(frames, threads)
+        cpu_baseline(frames, threads, side, args.d_model, args.dtype)
     times = []
     for _ in range(args.steps):
-        _, dt = cpu_baseline(frames, threads)
+        _, dt = cpu_baseline(frames, threads, side, args.d_model, args.dtype)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    val = frames * 1024 / (ms / 1e3) / 1e9
-    sample = f"BASELINE config 1 shape (32x32 tokens, d_model 320, fp32, 2 branches) at B'={frames} frames per step"
+    val = frames * side * side / (ms / 1e3) / 1e9
+    sample = (f"{frames} of the workload's {Bp} frames per step ({side}x{side} tokens each, d_model {args.d_model}, "
+              f"{args.dtype} I/O with fp32 scan arithmetic, 2 branches), oracle port of selective_scan_ref on {threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gtokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SS2D_cond_v10 layer forward on host CPU via the oracle port of selective_scan_ref",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(Bp, args.frames, args.cfg, side, args.d_model, args.params),
                    "sample": sample},
         "cpu_baseline": {"value": val, "unit": "Gtokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gtokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -259,19 +280,23 @@ def run_ours(args, rank, world, local_rank):
         with open(tpath) as f:
             ent = json.load(f).get("masked_scan config2 bf16 " + {0: "general", 1: "power"}[a_kind])
         traffic = ent["bytes"] if ent else None
+    FLOOR_CYCLES = {0: 129.0, 1: 117.0}
+    floor_ms = (updates / 16 / 32) * FLOOR_CYCLES[a_kind] / (148 * 4) / 1.965e9 * 1e3   # warp-steps over 592 schedulers
     cb = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        v, dt = cpu_baseline(14, threads)
+        # ~10-30 s of CPU work on a bounded sample of this workload: 2 of its frames (1 if a frame takes > 15 s)
+        _, t1 = cpu_baseline(1, threads, side, d_model, args.dtype)
+        nfr = 2 if t1 < 15.0 else 1
+        v, dt = cpu_baseline(nfr, threads, side, d_model, args.dtype) if nfr > 1 else (side * side / t1 / 1e9, t1)
         cb = {"value": v, "unit": "Gtokens/s", "cores": threads, "kind": "port", "seconds": dt,
-              "sample": "BASELINE config 1: B'=14 x 32x32 tokens, d_model 320, fp32, 2 branches, one pass"}
+              "sample": f"{nfr} of the workload's {Bp} frames ({side}x{side} tokens each, d_model {d_model}, {args.dtype} "
+                        "I/O with fp32 scan arithmetic, 2 branches), one pass after a 1-frame warm-up pass"}
     out = {
         "metric": METRIC, "value": tokens / (ms_step * 1e-3) / 1e9, "unit": "Gtokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if channel else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"SS2D_cond_v10 layer forward, BASELINE configs[1]: B'={Bp} ({args.frames} frames x CFG "
-                               f"{args.cfg}) x {side}x{side} tokens, d_model {d_model}, d_state 16, 2 branches x 2 "
-                               f"directions, all-ones masks, {args.params} parameters",
+        "config": {"workload": workload_name(Bp, args.frames, args.cfg, side, d_model, args.params),
                    "tokens_per_step_per_gpu": Bp * L, "l2": f"inputs rotate over {nrot} resident sets; per-step "
                    "working set (~1.5 GB) exceeds the 126 MB L2", "a_kind": {0: "general", 1: "power"}[a_kind],
                    "parallelism": (f"d_inner channel-sharded x{world}: replicated in_proj/x_proj, sliced scan, " +
@@ -283,17 +308,21 @@ def run_ours(args, rank, world, local_rank):
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": q, "kernel_ms": scan_ms, "state_updates_per_s": updates / (scan_ms * 1e-3),
                      "merge_ln_ms": merge_ms, "kernel_share_of_step": scan_ms / ms_step,
-                     # The scan is instruction-bound, not HBM-bound, at d_state 16.  General A: 19 MUFU
-                     # ops per channel-step x 8.1 SMSP-cycles each (measured MUFU.EX2 rate) = 154 cycles per warp-step,
-                     # a hard floor of this formulation.  S4D power path: the instruction mix saturates at 117 cycles
-                     # per warp-step at any occupancy (tools/microbench_step.cu, profiles/r01_microbench.txt).
+                     # The scan is instruction-bound, not HBM-bound, at d_state 16.  General A: the hot loop
+                     # holds 16 MUFU ops per channel-step (14 ex2 for the decays — one state pair runs on the FMA pipe —
+                     # plus softplus's ex2 and lg2; counted in the SASS) x 8.06 SMSP-cycles each (measured MUFU.EX2
+                     # rate) = 129 cycles per warp-step on the XU pipe.  S4D power path: 4 MUFU, FMA-pipe heavy; its
+                     # instruction mix saturates at 117 cycles per warp-step with no memory traffic at any occupancy
+                     # (tools/microbench_step.cu, profiles/r01_microbench.txt).
                      "instruction_floor": {
-                         "smsp_cycles_per_warp_step": {0: 154.0, 1: 117.0}[a_kind],
-                         "ms": (updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3,
-                         "frac_of_floor": ((updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9 * 1e3) / scan_ms,
+                         "smsp_cycles_per_warp_step": FLOOR_CYCLES[a_kind],
+                         "what": {0: "XU pipe: 16 MUFU per channel-step x 8.06 cycles (SASS count x measured rate)",
+                                  1: "measured saturation of the step's instruction mix (microbench_step)"}[a_kind],
+                         "ms": floor_ms,
+                         "frac_of_floor": floor_ms / scan_ms,
                          # the roofline fraction this kernel would show if it ran exactly at that floor: what
                          # fp32 per-(channel, state) exponentials allow on 148 SMs, whatever the memory system does
-                         "frac_at_floor": (q / peak / 1e9) / ((updates / 16 / 32) * {0: 154.0, 1: 117.0}[a_kind] / (148 * 4) / 1.965e9),
+                         "frac_at_floor": (q / peak / 1e6) / floor_ms,
                          "source": "profiles/r01_microbench.txt (B200 at 1965 MHz)"},
                      **{k + "_ms": v for k, v in extra.items()}},
         "e2e": {"value": tokens / (ms_e2e * 1e-3) / 1e9, "unit": "Gtokens/s",
