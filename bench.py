@@ -285,9 +285,10 @@ def run_ours(args, rank, world, local_rank):
     cb = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        # ~10-30 s of CPU work on a bounded sample of this workload: 2 of its frames (1 if a frame takes > 15 s)
+        # ~10-30 s of CPU work on a bounded sample of this workload: as many of its frames as ~15 s hold (a pass costs
+        # a fixed Python-loop part t1 plus ~0.3 t1 per extra frame), at least one
         _, t1 = cpu_baseline(1, threads, side, d_model, args.dtype)
-        nfr = 2 if t1 < 15.0 else 1
+        nfr = max(1, min(Bp, 1 + int((15.0 - t1) / (0.3 * t1)))) if t1 < 15.0 else 1
         v, dt = cpu_baseline(nfr, threads, side, d_model, args.dtype) if nfr > 1 else (side * side / t1 / 1e9, t1)
         cb = {"value": v, "unit": "Gtokens/s", "cores": threads, "kind": "port", "seconds": dt,
               "sample": f"{nfr} of the workload's {Bp} frames ({side}x{side} tokens each, d_model {d_model}, {args.dtype} "
