@@ -177,6 +177,23 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "Gtokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def bind_to_gpu_cpus(local_rank):
+    """N>1: run this rank on the CPU cores nearest its GPU (NVML's ideal affinity, cut to the cores the container
+    allows) so that the pinned staging buffers of the e2e path are first touched on the GPU's own NUMA node."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        ideal = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus = ideal & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:   # noqa: BLE001  (no NVML, or a container without the call: keep the inherited affinity)
+        pass
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from actalker_b200 import SS2D_cond_v10
@@ -200,6 +217,8 @@ def run_ours(args, rank, world, local_rank):
         inner = layer
     ones = torch.ones(1, 1, 576, 576, dtype=dtype, device=dev)
     masks = [ones, ones.clone()]
+    if world > 1 and not args.no_numa_bind:
+        bind_to_gpu_cpus(local_rank)   # before the pinned buffers are first touched
     hx, hid, hcd = host_inputs(Bp, L, d_model, dtype, SEED + 2 + (0 if channel else rank), pin=True)
     hy = torch.empty(Bp, L, d_model, dtype=dtype).pin_memory()
     # rotate over several resident input sets so no step finds its inputs in L2 (126 MB)
@@ -352,6 +371,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--params", default="init", choices=["init", "trained", "s4d"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: keep the inherited CPU affinity")
     ap.add_argument("--chain", type=int, default=None, help="force the number of chained chunks (tuning)")
     ap.add_argument("--shard", default="batch", choices=["batch", "channel"],
                     help="N>1: batch = weak scaling, no collective (default); channel = strong scaling of one call "
