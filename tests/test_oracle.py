@@ -208,3 +208,32 @@ def test_product_modules_have_the_reference_state_dict_layout():
         for k, v in sd.items():
             assert tuple(v.shape) == tuple(g["sd"][k].shape), (case, k)
         layer.load_state_dict({k: v.float() for k, v in g["sd"].items()}, strict=True)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle, rank 0 only) on a small shape: one JSON
+    line with the arm's metric / unit / workload, its own cpu_baseline block and an e2e block without copies; every
+    other rank of a torchrun launch exits 0 without printing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--d-model", "1280", "--frames", "2", "--gpus", "2"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "masked selective-scan Gtokens/s" and d["unit"] == "Gtokens/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["n_gpus"] == 2 and d["value"] > 0
+    assert "18x18 tokens, d_model 1280" in d["config"]["workload"] and "frames per step" in d["config"]["sample"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Gtokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["value"] - 2 * 324 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-9
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                        env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
