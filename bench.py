@@ -153,10 +153,16 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     side = int(72 / (args.d_model / 320))
     Bp = args.frames * args.cfg
-    _, t1 = cpu_baseline(1, threads, side, args.d_model, args.dtype)     # calibration pass (also warms torch)
-    budget = 240.0 / max(1, args.steps + args.warmup)
-    # a pass costs a fixed Python-loop part plus ~0.25 of it per extra frame (measured: 12.0 s / 14.5 s for 1 / 2 frames)
-    frames = max(1, min(Bp, 1 + int((budget - t1) / (0.3 * t1)))) if budget > t1 else 1
+    # two calibration passes (they also warm torch): a pass costs a fixed Python-loop part plus a per-frame part
+    # (B200 box, 16 cores: 1.5 s + 0.77 s per extra frame); then as many frames per step as keep the whole run near 200 s
+    _, t1 = cpu_baseline(1, threads, side, args.d_model, args.dtype)
+    budget = 200.0 / max(1, args.steps + args.warmup)
+    frames = 1
+    if Bp > 1 and budget > 1.5 * t1:
+        k = min(Bp, 3)
+        _, tk = cpu_baseline(k, threads, side, args.d_model, args.dtype)
+        per_frame = max((tk - t1) / (k - 1), 0.05 * t1)
+        frames = max(1, min(Bp, 1 + int((budget - t1) / per_frame)))
     for _ in range(args.warmup):
         cpu_baseline(frames, threads, side, args.d_model, args.dtype)
     times = []
