@@ -15,13 +15,13 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
            "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
            "actk_scan_algorithmic_bytes", "actk_peer_buffer_alloc", "actk_peer_buffer_free", "actk_peer_buffer_export",
-           "actk_peer_buffer_open", "actk_peer_buffer_close"]
+           "actk_peer_buffer_open", "actk_peer_buffer_close", "actk_gemm_tn_supported", "actk_gemm_tn_fwd"]
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -55,6 +55,15 @@ class MergeLnArgs(C.Structure):
                 ("gamma", _vp), ("beta", _vp), ("out", _vp), ("eps", _f),
                 ("n_branches", _i), ("Bp", _i), ("L", _i), ("D", _i), ("dtype", _i), ("layernorm", _i),
                 ("row_weight", _vp * 2), ("peer_out", _vp * 8), ("n_peers", _i), ("my_part", _i)]
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [("a", _vp), ("w", _vp), ("c", _vp), ("lda", _ll), ("ldw", _ll), ("ldc", _ll), ("plane_stride", _ll),
+                ("M", _i), ("N", _i), ("K", _i), ("planes", _i)]
+
+
+GEMM_MAX_PROBLEMS = 4
+GEMM_EPI_NONE, GEMM_EPI_SILU = 0, 1
 
 
 class LibraryMissing(RuntimeError):
@@ -115,9 +124,13 @@ def load():
     for name in ("actk_peer_buffer_alloc", "actk_peer_buffer_export", "actk_peer_buffer_open", "actk_peer_buffer_free",
                  "actk_peer_buffer_close"):
         getattr(lib, name).restype = _i
+    lib.actk_gemm_tn_supported.argtypes = [C.POINTER(GemmProblem), _i]
+    lib.actk_gemm_tn_supported.restype = _i
+    lib.actk_gemm_tn_fwd.argtypes = [C.POINTER(GemmProblem), _i, _i, _i, _vp]
+    lib.actk_gemm_tn_fwd.restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll
-    for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
+    for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd",
            "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_a_structure"):
         getattr(lib, name).restype = _i
     if lib.actk_abi_version() != ABI_VERSION:

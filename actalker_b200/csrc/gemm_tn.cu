@@ -1,0 +1,407 @@
+// Dense projections of the layer on the tensor cores (C-ABI entry actk_gemm_tn_fwd): C = epi(A @ W^T).
+//
+// Replaces, on the 16-bit route, every nn.Linear / einsum of SS2D_cond_v10.forward (reference
+// src/models/base/mamba_layer.py):
+//   :1960, :1966, :1977   id_proj / audio_proj / exp_proj + SiLU          (epilogue = SiLU of the rounded product)
+//   :1961, :1972          in_proj1 / in_proj2                             (one launch, x read once: stacked W, 2 output planes)
+//   :1521                 x_proj  einsum("b k d l, k c d -> b k c l")     (both directions as one N = 4*16 + 2*Rp product)
+//   :1523                 dt_proj einsum("b k r l, k d r -> b k d l")     (block-diagonal W over both directions)
+//   :1985                 out_proj
+// Same contraction and rounding points as the reference's GEMMs: fp32 accumulation, ONE rounding to the activation
+// dtype (and for the condition tokens SiLU evaluated on that rounded tensor and rounded again).
+//
+// All of these are skinny (K <= 1024, N <= 5120, M = B'*L = 129 600 at BASELINE config 2) and therefore HBM-bound: the
+// kernel is a streaming pipeline, not a flop machine.
+//   persistent CTAs, one per SM, 320 threads:
+//     warp 0     TMA producer: A (128 x 64) and W (BN x 64) slabs, SWIZZLE_128B, into a 4-6 deep shared-memory ring
+//     warp 1     one thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 16; SASS UTCHMMA) into one of TWO
+//                accumulator buffers in tensor memory (2 x 256 columns) and commits to the ring's / buffer's mbarriers
+//     warps 2-9  epilogue: tcgen05.ld (LDTM) of 32-column chunks (lane = row), rounding (+ SiLU), 16-byte stores into a
+//                64-byte-swizzled staging tile, TMA store (UTMASTG) of 32 x 32 boxes; the accumulator buffer is released
+//                as soon as it has been read, so tile i+1's MMAs run under tile i's stores
+// Up to 4 independent problems per launch (both branches, latent + tail tokens) share one grid through a tile table.
+// Tails of M / N / K need no special code: TMA zero-fills loads and clips stores at the tensor bounds.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace actk {
+
+constexpr int kGemmThreads = 320;
+constexpr int kBM = 128;               // rows per tile == MMA M
+constexpr int kBK = 64;                // K elements per slab: 128-byte rows, one SWIZZLE_128B atom wide
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kABytes = kBM * kBK * 2;
+constexpr uint32_t kEpiBytes = kEpiWarps * 2 * 2048;   // per warp: two 32 x 32 staging tiles of 16-bit elements
+constexpr int kMaxGemmProblems = ACTK_GEMM_MAX_PROBLEMS;
+
+struct GemmProblemDev {
+  CUtensorMap a, w, c;
+  int n_tiles;        // column tiles per row tile
+  int k_slabs;
+  int bn;             // columns per tile (multiple of 32, <= 256)
+  int tile_begin;     // index of this problem's first tile in the launch's tile table
+  int plane_cols;     // output columns per plane (N when the output is one tensor)
+  int M, N;
+};
+struct alignas(64) GemmParams {
+  GemmProblemDev p[kMaxGemmProblems];
+  int n_problems, total_tiles, stages, epilogue;
+  uint32_t stage_bytes;
+};
+
+__device__ __forceinline__ uint64_t gemm_sw128_desc(uint32_t smem_addr) {   // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void gemm_tma_load_2d(uint32_t dst_smem, const void *tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void gemm_tma_store_3d(const void *tmap, int c0, int c1, int c2, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(c2), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void gemm_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gemm_bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gemm_bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gemm_bar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(kSuspendHintNs)
+      : "memory");
+}
+__device__ __forceinline__ void gemm_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void gemm_commit(uint32_t bar) {   // arrives once every MMA issued so far by this thread is done
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gemm_tmem_ld16(uint32_t taddr, uint32_t *r) {   // no wait: see gemm_tmem_wait32
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void gemm_tmem_wait32(uint32_t *r) {   // ties all 32 registers to the wait
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// which problem owns tile t (at most 4 problems: a compare chain)
+__device__ __forceinline__ int gemm_problem_of(const GemmParams &P, int t) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGemmProblems; ++i)
+    if (i < P.n_problems && t >= P.p[i].tile_begin) g = i;
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t gemm_smem[];
+  const uint32_t base = (smem_u32(gemm_smem) + 1023u) & ~1023u;     // SWIZZLE_128B atoms want 1024-byte alignment
+  const int S = P.stages;
+  const uint32_t epi_base = base + (uint32_t)S * P.stage_bytes;
+  const uint32_t bar_base = epi_base + kEpiBytes;
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * S, tfull_bar = bar_base + 16 * S,
+                 tempty_bar = tfull_bar + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gemm_smem + (tempty_bar + 16 - smem_u32(gemm_smem)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { gemm_bar_init(full_bar + 8 * s, 1); gemm_bar_init(empty_bar + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { gemm_bar_init(tfull_bar + 8 * b, 1); gemm_bar_init(tempty_bar + 8 * b, kEpiWarps); }
+    mbar_fence_init();
+    for (int g = 0; g < P.n_problems; ++g) { tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); }
+  }
+  __syncwarp();
+  if (warp == 1) {   // 2 accumulator buffers x 256 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---------------------------------------------------------------- TMA producer
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
+        const int local = tile - pr.tile_begin;
+        const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
+        const uint32_t tx = kABytes + (uint32_t)pr.bn * (kBK * 2);
+        for (int ks = 0; ks < pr.k_slabs; ++ks, ++it) {
+          const uint32_t s = it % S, use = it / S;
+          if (use > 0) gemm_bar_wait(empty_bar + 8 * s, (use - 1) & 1);
+          const uint32_t sa = base + s * P.stage_bytes;
+          gemm_bar_expect_tx(full_bar + 8 * s, tx);
+          gemm_tma_load_2d(sa, &pr.a, ks * kBK, m * kBM, full_bar + 8 * s);
+          gemm_tma_load_2d(sa + kABytes, &pr.w, ks * kBK, n * pr.bn, full_bar + 8 * s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---------------------------------------------------------------- MMA issuer
+      uint32_t it = 0, tc = 0;
+      constexpr uint32_t fmt = IO<T>::is_bf16 ? 1u : 0u;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+        const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(pr.bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint32_t b = tc & 1, ub = tc >> 1;
+        if (ub > 0) gemm_bar_wait(tempty_bar + 8 * b, (ub - 1) & 1);   // the epilogue has read this buffer's previous tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem + b * 256;
+        for (int ks = 0; ks < pr.k_slabs; ++ks, ++it) {
+          const uint32_t s = it % S, use = it / S;
+          gemm_bar_wait(full_bar + 8 * s, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * P.stage_bytes, sw = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            gemm_umma(acc, gemm_sw128_desc(sa + k * 32), gemm_sw128_desc(sw + k * 32), idesc, (uint32_t)((ks | k) != 0));
+          gemm_commit(empty_bar + 8 * s);    // the slab may be overwritten once these MMAs have read it
+        }
+        gemm_commit(tfull_bar + 8 * b);      // accumulators of this tile complete
+      }
+    }
+    __syncwarp();
+  } else {             // ---------------------------------------------------------------- epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;                  // tensor-memory lane quadrant this warp may read: warp id % 4
+    const int h = ew >> 2;                   // which half of the 32-column chunks
+    const uint32_t stage0 = epi_base + (uint32_t)ew * 4096;
+    uint32_t tc = 0, chunk_count = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+      const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
+      const int local = tile - pr.tile_begin;
+      const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
+      const uint32_t b = tc & 1, ub = tc >> 1;
+      gemm_bar_wait(tfull_bar + 8 * b, ub & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row0 = m * kBM + q * 32;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256;
+      for (int c = h; c < pr.bn / 32; c += 2) {
+        const int col = n * pr.bn + c * 32;
+        uint32_t r[32];
+        gemm_tmem_ld16(trow + c * 32, r);
+        gemm_tmem_ld16(trow + c * 32 + 16, r + 16);
+        gemm_tmem_wait32(r);
+        if (col >= pr.N || row0 >= pr.M) continue;          // nothing of this chunk lies inside the output
+        uint4 v[4];
+        T *e = reinterpret_cast<T *>(v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float f = __uint_as_float(r[i]);
+          if (P.epilogue == ACTK_GEMM_EPI_SILU) f = silu(IO<T>::rnd(f));   // act(Linear(x)): the product is a `dtype` tensor first
+          IO<T>::st(e + i, f);
+        }
+        const uint32_t buf = stage0 + (chunk_count & 1) * 2048;
+        ++chunk_count;
+        if (lane == 0) bulk_wait_read<1>();                  // the store issued from this buffer two chunks ago has read it
+        __syncwarp();
+        // staging tile: 32 rows x 64 bytes, SWIZZLE_64B (16-byte piece j of row r at (j ^ ((r >> 1) & 3)))
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t addr = buf + (uint32_t)lane * 64 + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w)
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int plane = col / pr.plane_cols;
+          gemm_tma_store_3d(&pr.c, col - plane * pr.plane_cols, row0, plane, buf);
+          bulk_commit();
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) gemm_bar_arrive(tempty_bar + 8 * b);    // this warp's reads of the buffer are done
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*GemmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static GemmEncodeFn gemm_encode_fn() {
+  static GemmEncodeFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<GemmEncodeFn>(p);
+  }
+  return fn;
+}
+
+// column-tile width: the fewest tiles of at most 256 columns, then the least padding; multiples of 32; when the output
+// is split into planes a tile must not straddle two of them
+static int gemm_pick_bn(int N, int plane_cols) {
+  const int span = plane_cols;                         // tiles are laid out per plane
+  int best = 32, best_tiles = 1 << 30, best_pad = 1 << 30;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (plane_cols != N && span % bn != 0) continue;
+    const int tiles = (span + bn - 1) / bn, pad = tiles * bn - span;
+    if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best = bn; best_tiles = tiles; best_pad = pad; }
+  }
+  return best;
+}
+
+static const char *gemm_check(const actk_gemm_problem &p, int es) {
+  if (!p.a || !p.w || !p.c) return "NULL pointer";
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "non-positive size";
+  if (p.lda < p.K || p.ldw < p.K) return "row pitch smaller than K";
+  if (p.planes < 1 || p.N % p.planes != 0) return "N is not a multiple of planes";
+  const int pc = p.N / p.planes;
+  if (p.ldc < pc) return "ldc smaller than the columns of a plane";
+  if (p.planes > 1 && pc % 32 != 0) return "columns per plane must be a multiple of 32 when planes > 1";
+  if ((p.lda * es) % 16 || (p.ldw * es) % 16 || (p.ldc * es) % 16 || (p.plane_stride * es) % 16) return "row pitch not a multiple of 16 bytes";
+  if ((reinterpret_cast<uintptr_t>(p.a) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.c)) & 15)
+    return "pointer not aligned to 16 bytes";
+  return nullptr;
+}
+
+template <typename T>
+static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, int epilogue, cudaStream_t stream) {
+  GemmEncodeFn fn = gemm_encode_fn();
+  if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
+  const CUtensorMapDataType dt = dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_problems = n;
+  P.epilogue = epilogue;
+  int tiles = 0, bn_max = 32;
+  for (int g = 0; g < n; ++g) {
+    const actk_gemm_problem &p = pr[g];
+    GemmProblemDev &d = P.p[g];
+    const int pc = p.N / p.planes;
+    d.bn = gemm_pick_bn(p.N, pc);
+    d.plane_cols = pc;
+    d.M = p.M; d.N = p.N;
+    d.k_slabs = (p.K + kBK - 1) / kBK;
+    d.n_tiles = p.planes * ((pc + d.bn - 1) / d.bn);
+    d.tile_begin = tiles;
+    tiles += ((p.M + kBM - 1) / kBM) * d.n_tiles;
+    bn_max = d.bn > bn_max ? d.bn : bn_max;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    {   // A (K, M): slabs of 64 x 128
+      cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+      cuuint64_t strides[1] = {(cuuint64_t)p.lda * sizeof(T)};
+      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+      CUresult r = fn(&d.a, dt, 2, const_cast<void *>(p.a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (A of problem %d) failed with CUresult %d", g, (int)r);
+    }
+    {   // W (K, N): slabs of 64 x bn; with planes the tile (plane, j) covers rows plane*pc + j*bn of the stacked weight
+      cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
+      cuuint64_t strides[1] = {(cuuint64_t)p.ldw * sizeof(T)};
+      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)d.bn};
+      CUresult r = fn(&d.w, dt, 2, const_cast<void *>(p.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (W of problem %d) failed with CUresult %d", g, (int)r);
+    }
+    {   // C (plane_cols, M, planes): the epilogue stores 32 x 32 boxes
+      cuuint64_t dims[3] = {(cuuint64_t)pc, (cuuint64_t)p.M, (cuuint64_t)p.planes};
+      cuuint64_t strides[2] = {(cuuint64_t)p.ldc * sizeof(T),
+                               (cuuint64_t)(p.planes > 1 ? p.plane_stride : (long long)p.ldc * p.M) * sizeof(T)};
+      cuuint32_t box[3] = {32, 32, 1};
+      CUresult r = fn(&d.c, dt, 3, p.c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (C of problem %d) failed with CUresult %d", g, (int)r);
+    }
+  }
+  P.total_tiles = tiles;
+  P.stage_bytes = kABytes + (uint32_t)bn_max * (kBK * 2);
+  const size_t fixed = 1024 + kEpiBytes + 16 * 6 + 64;
+  int dev = 0, sms = 0, smem_max = 0;
+  ACTK_CUDA_OK(cudaGetDevice(&dev));
+  ACTK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ACTK_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int stages = (int)(((size_t)smem_max - fixed) / P.stage_bytes);
+  stages = stages > 6 ? 6 : stages;
+  if (stages < 2) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: %d bytes of shared memory per block do not hold two pipeline stages", smem_max);
+  P.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * P.stage_bytes + kEpiBytes + 16 * (size_t)stages + 64;
+  auto kern = gemm_tn_kernel<T>;
+  static int configured[64] = {};   // per device: the largest dynamic shared memory size requested so far
+  if (dev < 64 && configured[dev] < (int)smem) {
+    ACTK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    configured[dev] = smem_max;
+  }
+  kern<<<tiles < sms ? tiles : sms, kGemmThreads, smem, stream>>>(P);
+  ACTK_CUDA_OK(cudaGetLastError());
+  return ACTK_OK;
+}
+
+}  // namespace actk
+
+using namespace actk;
+
+extern "C" int actk_gemm_tn_supported(const actk_gemm_problem *p, int dtype) {
+  if (!p || (dtype != ACTK_F16 && dtype != ACTK_BF16)) return 0;
+  return gemm_check(*p, 2) == nullptr;
+}
+
+extern "C" int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, int epilogue, void *stream) {
+  if (!problems) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: problems is NULL");
+  if (n_problems < 1 || n_problems > kMaxGemmProblems)
+    ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: n_problems=%d (1..%d per launch)", n_problems, kMaxGemmProblems);
+  if (dtype != ACTK_F16 && dtype != ACTK_BF16)
+    ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "gemm_tn: dtype=%d (the tensor-core route is f16 / bf16; fp32 projections stay with the caller)", dtype);
+  if (epilogue != ACTK_GEMM_EPI_NONE && epilogue != ACTK_GEMM_EPI_SILU) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: epilogue=%d", epilogue);
+  for (int g = 0; g < n_problems; ++g) {
+    const char *why = gemm_check(problems[g], 2);
+    if (why) {
+      const actk_gemm_problem &p = problems[g];
+      const bool align = strstr(why, "16 bytes") != nullptr;
+      ACTK_FAIL(align ? ACTK_ERR_BAD_ALIGN : (strstr(why, "NULL") ? ACTK_ERR_BAD_ARG : ACTK_ERR_BAD_SHAPE),
+                "gemm_tn: problem %d (M=%d N=%d K=%d lda=%lld ldw=%lld ldc=%lld planes=%d): %s", g, p.M, p.N, p.K, p.lda, p.ldw,
+                p.ldc, p.planes, why);
+    }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ACTK_F16) return launch_gemm<__half>(problems, n_problems, dtype, epilogue, st);
+  return launch_gemm<__nv_bfloat16>(problems, n_problems, dtype, epilogue, st);
+}

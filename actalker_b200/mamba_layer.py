@@ -7,12 +7,15 @@ Same constructor arguments, same `forward(x, id_emb, conds, masks)`, same parame
 (SURVEY.md Appendix C), so `unet.load_state_dict(strict=True)` (Inference.py:124-127) and the fp32 re-cast of
 `A_logs | Ds | dt_projs_bias` (Inference.py:430-433) keep working unchanged.
 
-What runs where
-    cuBLAS (via torch): in_proj1/2, id/audio/exp projections, x_proj, dt_proj, out_proj — dense GEMMs, the
-        same contractions and 16-bit rounding points as the reference's nn.Linear / einsum calls.
-    this repo's kernels (C-ABI, include/actalker_b200.h):
+What runs where (16-bit activations — the reference's inference dtype; everything is this repo's CUDA, C-ABI
+include/actalker_b200.h):
+        actk_gemm_tn_fwd           in_proj1/2, id/audio/exp projections (+SiLU), x_proj, dt_proj, out_proj: persistent
+                                   TMA + tcgen05 kernel, same contractions and rounding points as the reference's
+                                   nn.Linear / einsum calls                                    (:1960-1961, :1521-1523, :1985)
         actk_masked_scan_fwd       gather -> tail concat -> both scan directions -> scatter   (:1963-1970, :1505-1548)
         actk_merge_layernorm_fwd   direction sum, passthrough rows, branch sum, out_norm      (:1542-1547, :1983-1984)
+    fp32 activations: the projections stay fp32 GEMMs in torch (tensor cores would round the operands; the reference's own
+    arithmetic for that dtype); the scan and merge kernels are the same.  ACTK_TC_GEMM=0 forces the torch GEMMs.
 The mask -> index computation is the reference's own expression, cached per mask (mask.py).
 Forward only: inference runs under no_grad (pipeline ...two_ip.py:351); backward is not built.
 """
@@ -28,6 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from . import gemm
 from .mask import MaskIndex, MaskIndexCache
 from .selective_scan_interface import _DTYPES, _ptr, _stream, a_kind_of
 
@@ -71,6 +75,8 @@ FUSE_LN_OUT_PROJ = os.environ.get("ACTK_FUSE_LN_OUT", "0") == "1"
 BATCH_IN_PROJ = os.environ.get("ACTK_BATCH_IN_PROJ", "1") != "0"   # one batched GEMM for in_proj1 / in_proj2
 _SIDE_STREAMS = {}
 SIDE_STREAM = os.environ.get("ACTK_SIDE_STREAM", "1") != "0"
+# 16-bit activations: the dense projections run on this repo's tcgen05 kernel (gemm.py); "0" routes them to torch.
+TC_GEMM = os.environ.get("ACTK_TC_GEMM", "1") != "0"
 
 
 class _Fork:
@@ -81,7 +87,9 @@ class _Fork:
     def __init__(self, device):
         self.main = torch.cuda.current_stream(device)
         if SIDE_STREAM:
-            key = (device.index if device.index is not None else torch.cuda.current_device())
+            # one side stream per (device, calling stream): a fork only waits for ITS main stream, so sharing a side
+            # stream between callers on different streams would let one call reuse side-pool blocks another still reads
+            key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream)
             if key not in _SIDE_STREAMS:
                 _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
             self.side = _SIDE_STREAMS[key]
@@ -132,7 +140,7 @@ FUSE_DT_PROJ = os.environ.get("ACTK_FUSE_DT", "0") == "1"
 
 def _rank_pad(R: int):
     """(padded rank, fusable): the dt_proj input of each direction occupies a block of `padded rank` x_dbl columns.
-    Ranks up to 80 (d_model <= 1280 with dt_rank='auto') round up to a width the in-kernel mma.sync dt_proj handles."""
+    Ranks up to 80 (d_model <= 1280 with dt_rank='auto') round up to a width the in-kernel tcgen05 dt_proj handles."""
     for ks in _FUSED_KSLABS:
         if R <= 16 * ks:
             return 16 * ks, True
@@ -227,6 +235,28 @@ class SS2D_Unit(nn.Module):
         self._derived, self._derived_key = d, key
         return d
 
+    def weights_for(self, dtype, lo: int = 0, hi: int = None):
+        """Per-(activation dtype, channel slice) views of the derived weights, cached beside them (rebuilt when a
+        parameter changes): no cast, slice or gather kernel runs per call, so nothing the side stream consumes is ever
+        produced by fresh main-stream work.
+          w_xproj (xw, D)       x_proj rows [B_0|C_0|B_1|C_1|dt_0|dt_1]
+          w_dt    (2Rp, 2Dk)    block-diagonal dt_proj, torch.mm form (fp32 route)
+          w_dt_nk (2Dk, 2Rp)    the same as an nn.Linear weight (tensor-core route)
+          A (2Dk, N), Ds, dt_bias (2Dk) fp32"""
+        dv = self.derived()
+        D = self.d_inner
+        hi = D if hi is None else hi
+        key = ("weights", dtype, lo, hi)
+        if key not in dv:
+            with torch.no_grad():
+                w_dt, A, Ds, dtb = dv["w_dt"], dv["A"], dv["Ds"], dv["dt_bias"]
+                if (lo, hi) != (0, D):   # columns / rows [k*D + lo, k*D + hi) of both directions
+                    cols = torch.cat([torch.arange(k * D + lo, k * D + hi, device=A.device) for k in range(2)])
+                    w_dt, A, Ds, dtb = w_dt[:, cols], A[cols].contiguous(), Ds[cols].contiguous(), dtb[cols].contiguous()
+                dv[key] = {"w_xproj": dv["w_xproj"].to(dtype).contiguous(), "w_dt": w_dt.to(dtype).contiguous(),
+                           "w_dt_nk": w_dt.t().to(dtype).contiguous(), "A": A, "Ds": Ds, "dt_bias": dtb}
+        return dv[key]
+
     def dt_image(self, lo: int, hi: int, dtype) -> torch.Tensor:
         """Tensor-core operand image of dt_projs_weight[:, lo:hi] for the fused dt_proj (actk_pack_dt_proj_weight),
         cached with the other derived weights (rebuilt when a parameter changes)."""
@@ -286,12 +316,16 @@ def auto_segments(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
 
 
 def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None, ch_slice=None):
-    """Shared launcher: x_proj / dt_proj GEMMs (cuBLAS) + one actk_masked_scan_fwd for all given branches.
+    """Shared launcher: x_proj / dt_proj of every branch + one actk_masked_scan_fwd for all given branches.
     xzs[i]: (Bp, L, D) contiguous; tails[i]: (Bp, n_tail, D) or None; idxs[i]: int32 (n_sel,).
     ch_slice=(lo, hi): scan only channels [lo, hi) of every direction (multi-GPU channel sharding): x_proj still
     contracts over all D channels (B|C are replicated), delta / A / D / dt_bias / u are sliced.
     Returns per-branch (ydir (2, Bp, L, Dk), xz_k (Bp, L, Dk)) with Dk = hi - lo (D when unsliced); rows of
-    unselected tokens of ydir are uninitialised."""
+    unselected tokens of ydir are uninitialised.
+
+    16-bit activations: the projections of ALL branches (latent and tail tokens) are two launches of this repo's
+    tensor-core kernel (gemm.py) — x_proj, then dt_proj reading the dt columns of x_dbl in place.  fp32: torch GEMMs,
+    the tail tokens' small ones on a side stream."""
     lib = _lib.load()
     x0 = xzs[0]
     if not x0.is_cuda:
@@ -302,10 +336,13 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
     lo, hi = (0, D) if ch_slice is None else ch_slice
     Dk = hi - lo
     sliced = Dk != D
+    tc = TC_GEMM and gemm.usable(*xzs, *tails) and D % 8 == 0
     args = _lib.MaskedScanArgs()
     args.n_branches, args.Bp, args.L, args.D, args.N = len(units), Bp, L, Dk, _N
     args.dtype = _DTYPES[x0.dtype]
-    keep, outs = [], []
+    keep, outs, jobs = [], [], []
+    fork = None if tc else _Fork(x0.device)
+    xproj = []                              # tensor-core route: x_proj problems of every branch, one launch
     for i, unit in enumerate(units):
         dv = unit.derived()
         xz, tail, n_sel = xzs[i], tails[i], n_sels[i]
@@ -320,50 +357,72 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         if n_sel == 0:
             continue
         xw = dv["xw"]
-        w_x = dv["w_xproj"].to(xz.dtype)
-        fork = _Fork(xz.device)
-        with fork:                                                         # tail tokens: side stream
-            xdbl_tail = F.linear(tail, w_x) if n_tail else None            # (Bp, n_tail, xw)
+        w = unit.weights_for(xz.dtype, lo, hi)
+        w_x = w["w_xproj"]
+        fused = FUSE_DT_PROJ and dv["fusable"] and xz.element_size() == 2
         # x_proj of the SELECTED tokens only, in sequence order (row p <-> latent token idx[p]).  Under a partial mask
         # the rows are gathered first when few are selected (the GEMM shrinks with them), else projected in place and
         # the narrow x_dbl rows gathered afterwards.
-        if n_sel == L:
-            xdbl = F.linear(xz, w_x)                                       # (Bp, L, xw)
-        else:
-            sel64 = idx64s[i] if idx64s is not None else idxs[i].long()
-            if 2 * n_sel <= L:
-                xdbl = F.linear(xz.index_select(1, sel64), w_x)            # (Bp, n_sel, xw)
+        sel64 = None if n_sel == L else (idx64s[i] if idx64s is not None else idxs[i].long())
+        gather_after = sel64 is not None and 2 * n_sel > L
+        src = xz if (sel64 is None or gather_after) else xz.index_select(1, sel64)
+        job = {"i": i, "unit": unit, "w": w, "xw": xw, "fused": fused, "n_sel": n_sel, "n_tail": n_tail, "tail": tail,
+               "sel64": sel64 if gather_after else None, "ydir": ydir, "xz_k": xz_k, "src": src}
+        if tc:
+            job["xdbl"] = torch.empty((Bp, src.shape[1], xw), dtype=xz.dtype, device=xz.device)
+            xproj.append(gemm.Problem(src.view(-1, D), w_x, job["xdbl"].view(-1, xw)))
+            if n_tail:
+                job["xdbl_tail"] = torch.empty((Bp, n_tail, xw), dtype=xz.dtype, device=xz.device)
+                xproj.append(gemm.Problem(tail.view(-1, D), w_x, job["xdbl_tail"].view(-1, xw)))
             else:
-                xdbl = F.linear(xz, w_x).index_select(1, sel64)
-        A, Dsk, dtb = dv["A"], dv["Ds"], dv["dt_bias"]
-        fused = FUSE_DT_PROJ and dv["fusable"] and xz.element_size() == 2
-        w_dt = unit.dt_image(lo, hi, xz.dtype) if fused else dv["w_dt"].to(xz.dtype)
-        if sliced:   # columns / rows [k*D + lo, k*D + hi) of both directions
-            cols = torch.cat([torch.arange(k * D + lo, k * D + hi, device=xz.device) for k in range(2)])
-            A, Dsk, dtb = A[cols].contiguous(), Dsk[cols].contiguous(), dtb[cols].contiguous()
-            w_dt = w_dt if fused else w_dt[:, cols].contiguous()
-            tail = None if tail is None else tail[..., lo:hi].contiguous()
-        delta = delta_tail = None
-        if not fused:
-            # dt_proj as one GEMM over both directions (block-diagonal weight).  The dt columns of x_dbl are read in
-            # place as a strided 2-D operand (lda = xw): no copy of the (Bp*L, 2Rp) slice, and the tail rows get their
-            # own small GEMM instead of a concatenation.  Rows are in sequence order: row p <-> latent token idx[p].
-            dtr2d = xdbl.view(Bp * n_sel, xw)[:, 4 * _N:]
-            with fork(wait=sliced):    # sliced: w_dt was just cut on the current stream
-                delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w_dt).view(Bp, n_tail, 2 * Dk) if n_tail else None
-            delta = torch.mm(dtr2d, w_dt).view(Bp, n_sel, 2 * Dk)
-        fork.join(xdbl_tail, delta_tail)
-        # fused: the scan kernel multiplies each 16-token tile of dt columns by w_dt on the tensor cores itself
-        # (tcgen05.mma, fp32 accumulate, one rounding to the activation dtype) — no delta tensor, no dt_proj launch
-        rp = dv["rank_pad"] if fused else 0
+                job["xdbl_tail"] = None
+        else:
+            with fork:                                                         # tail tokens: side stream
+                job["xdbl_tail"] = F.linear(tail, w_x) if n_tail else None     # (Bp, n_tail, xw)
+            job["xdbl"] = F.linear(src, w_x)
+        jobs.append(job)
+    if tc:
+        gemm.run(xproj, name="gemm_xproj")
+    dtproj = []
+    for job in jobs:
+        i, w, xw, n_sel, n_tail, tail = job["i"], job["w"], job["xw"], job["n_sel"], job["n_tail"], job["tail"]
+        xdbl, xdbl_tail, fused = job["xdbl"], job["xdbl_tail"], job["fused"]
+        if job["sel64"] is not None:
+            xdbl = xdbl.index_select(1, job["sel64"])                          # (Bp, n_sel, xw), sequence order
+        if sliced and tail is not None:
+            tail = tail[..., lo:hi].contiguous()
+        delta = delta_tail = w_img = None
+        if fused:
+            # the scan kernel multiplies each 16-token tile of dt columns by w_dt on the tensor cores itself
+            # (tcgen05.mma, fp32 accumulate, one rounding to the activation dtype) — no delta tensor, no dt_proj launch
+            w_img = job["unit"].dt_image(lo, hi, xdbl.dtype)
+        elif tc:
+            # dt_proj of both directions as one product with the block-diagonal weight; the dt columns of x_dbl are
+            # read in place (row pitch xw) — no copy of the (Bp*n_sel, 2Rp) slice, and the tail rows are one more
+            # problem of the same launch instead of a concatenation.  Rows are in sequence order.
+            delta = torch.empty((Bp, n_sel, 2 * Dk), dtype=xdbl.dtype, device=xdbl.device)
+            dtproj.append(gemm.Problem(xdbl.view(-1, xw)[:, 4 * _N:], w["w_dt_nk"], delta.view(-1, 2 * Dk)))
+            if n_tail:
+                delta_tail = torch.empty((Bp, n_tail, 2 * Dk), dtype=xdbl.dtype, device=xdbl.device)
+                dtproj.append(gemm.Problem(xdbl_tail.view(-1, xw)[:, 4 * _N:], w["w_dt_nk"], delta_tail.view(-1, 2 * Dk)))
+        else:
+            with fork(wait=False):    # depends on side-stream work and cached weights only
+                delta_tail = torch.mm(xdbl_tail.view(Bp * n_tail, xw)[:, 4 * _N:], w["w_dt"]).view(Bp, n_tail, 2 * Dk) if n_tail else None
+            delta = torch.mm(xdbl.view(Bp * n_sel, xw)[:, 4 * _N:], w["w_dt"]).view(Bp, n_sel, 2 * Dk)
+        rp = job["unit"].derived()["rank_pad"] if fused else 0
         if args.xw not in (0, xw) or (args.xw != 0 and args.dt_rank_pad != rp):
             raise RuntimeError("branches disagree on the x_proj width / dt rank")
         args.xw, args.dt_rank_pad = xw, rp
-        b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(xz_k), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
+        b = args.br[i]
+        b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(job["xz_k"]), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
         b.delta_tail = _ptr(delta_tail)
-        b.w_dt = _ptr(w_dt) if fused else None
-        b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(A), _ptr(Dsk), _ptr(dtb), _ptr(ydir)
-        keep += [xdbl, xdbl_tail, delta, delta_tail, w_x, w_dt, A, Dsk, dtb, tail, xz_k]
+        b.w_dt = _ptr(w_img) if fused else None
+        b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(w["A"]), _ptr(w["Ds"]), _ptr(w["dt_bias"]), _ptr(job["ydir"])
+        keep += [xdbl, xdbl_tail, delta, delta_tail, w_img, tail, job]
+    if tc:
+        gemm.run(dtproj, name="gemm_dtproj")
+    elif jobs:
+        fork.join()
     live = [i for i, n in enumerate(n_sels) if n > 0]
     if live:
         min_tiles = min(-(-(n_sels[i] + (0 if tails[i] is None else tails[i].shape[1])) // 16) for i in live)
@@ -461,7 +520,14 @@ class SS2D_cond_v10(nn.Module):
             return y
         with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
-        return self.out_proj(out) if out_proj else out
+        return self._out_proj(out) if out_proj else out
+
+    def _out_proj(self, y):
+        """out_proj (mamba_layer.py:1985): tensor-core kernel for 16-bit activations, torch otherwise."""
+        w = self.out_proj.weight
+        if TC_GEMM and self.out_proj.bias is None and gemm.usable(y, w) and y.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
+            return gemm.linear(y, w, name="gemm_outproj")
+        return self.out_proj(y)
 
     use_id = True   # SS2D_cond_v10_wo_id drops the identity token (and has no id_proj)
 
@@ -471,24 +537,59 @@ class SS2D_cond_v10(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("actalker_b200 layers run on CUDA tensors only (no CPU path)")
         L = x.shape[1]
-        audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
-        m1 = self.mask_cache.get(masks[0], L)
-        m2 = self.mask_cache.get(masks[1], L)
+        # the index lists live on the activations' device wherever the mask tensors are (a CPU mask works upstream
+        # too: indexing moves the index tensor); the downsample itself runs on the mask's own device and dtype
+        m1 = self.mask_cache.get(masks[0], L, device=x.device)
+        m2 = self.mask_cache.get(masks[1], L, device=x.device)
         fork = _Fork(x.device)
         with fork:                                   # 35 id / condition tokens per frame: side stream
-            tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
-            if self.use_id:
-                id_tok = self.act2(self.id_proj(id_emb))
-                tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
-            tail1, tail2 = tail1.contiguous(), tail2.contiguous()
+            tail1, tail2 = self._tail_tokens(id_emb, conds)
         xz1, xz2 = self._in_proj_both(x)             # the latent tokens: current stream
         fork.join(tail1, tail2)
         return xz1, xz2, tail1, tail2, m1, m2
 
+    def _tc_ok(self, *acts):
+        """16-bit CUDA activations and weights of the same dtype, no biases, 16-byte rows: the tensor-core route."""
+        ws = [self.in_proj1.weight, self.in_proj2.weight, self.audio_proj.weight, self.exp_proj.weight]
+        if self.use_id:
+            ws.append(self.id_proj.weight)
+        lins = [self.in_proj1, self.in_proj2, self.audio_proj, self.exp_proj] + ([self.id_proj] if self.use_id else [])
+        return (TC_GEMM and gemm.usable(*acts, *ws) and all(l.bias is None for l in lins)
+                and self.d_model % 8 == 0 and self.d_cond % 8 == 0)
+
+    def _tail_tokens(self, id_emb, conds):
+        """tail1 = [SiLU(id_proj(id)), SiLU(audio_proj(audio tokens))], tail2 = [SiLU(id_proj(id)), SiLU(exp_proj(exp token))]
+        (mamba_layer.py:1958-1960, 1966, 1977).  Tensor-core route: the products are written straight into the two tail
+        buffers — `conds` holds 32 audio tokens then the expression token per frame, tail1 the id token then the 32 audio
+        tokens, so audio_proj over ALL rows of `conds`, stored one row further down, puts every audio token in place; the
+        rows it also fills with the (meaningless) audio projection of the expression token are exactly the id slots,
+        which the id_proj launch that follows overwrites."""
+        Bp, n_c, dc = conds.shape
+        D = self.d_inner
+        if self.use_id and n_c >= 2 and self._tc_ok(id_emb, conds) and conds.is_contiguous():
+            tail1 = torch.empty((Bp, n_c, D), dtype=conds.dtype, device=conds.device)
+            tail2 = torch.empty((Bp, 2, D), dtype=conds.dtype, device=conds.device)
+            flat = conds.view(Bp * n_c, dc)
+            gemm.run([gemm.Problem(flat[:-1], self.audio_proj.weight, tail1.view(Bp * n_c, D)[1:]),
+                      gemm.Problem(conds[:, -1, :], self.exp_proj.weight, tail2[:, 1, :])], silu=True, name="gemm_cond")
+            idm = id_emb.reshape(Bp, dc)
+            gemm.run([gemm.Problem(idm, self.id_proj.weight, tail1[:, 0, :]),
+                      gemm.Problem(idm, self.id_proj.weight, tail2[:, 0, :])], silu=True, name="gemm_cond")
+            return tail1, tail2
+        audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
+        if not self.use_id and self._tc_ok(conds):           # v10_wo_id: no id slot to absorb the shifted store
+            return (gemm.linear(audio_cond, self.audio_proj.weight, silu=True, name="gemm_cond"),
+                    gemm.linear(exp_cond, self.exp_proj.weight, silu=True, name="gemm_cond"))
+        tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
+        if self.use_id:
+            id_tok = self.act2(self.id_proj(id_emb))
+            tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
+        return tail1.contiguous(), tail2.contiguous()
+
     def _in_proj_both(self, x):
-        """in_proj1(x), in_proj2(x) (mamba_layer.py:1960-1961) as ONE batched GEMM: x enters as a stride-0 batch of two,
-        the weights as a (2, d_model, D) stack, and the two results come out as separate contiguous tensors — x is
-        read once per call instead of once per branch (cuBLAS, config 2: 110 us against 140 us for the two calls)."""
+        """in_proj1(x), in_proj2(x) (mamba_layer.py:1960-1961) as ONE product: the two weights stacked to (2D, d_model),
+        the two results written as separate contiguous planes — x is read once per call instead of once per branch.
+        Tensor-core route (16-bit): one actk_gemm_tn_fwd launch; fp32: one batched torch GEMM over a stride-0 batch."""
         w1, w2 = self.in_proj1.weight, self.in_proj2.weight
         if (not BATCH_IN_PROJ or self.in_proj1.bias is not None or self.in_proj2.bias is not None or w1.dtype != x.dtype
                 or w2.dtype != x.dtype):
@@ -496,11 +597,21 @@ class SS2D_cond_v10(nn.Module):
         key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.dtype, str(w1.device))
         if getattr(self, "_w_in_key", None) != key:
             with torch.no_grad():
-                self._w_in = torch.stack([w1.t(), w2.t()], dim=0).contiguous()      # (2, d_model, D)
+                self._w_in = torch.stack([w1.t(), w2.t()], dim=0).contiguous()      # (2, d_model, D): torch.bmm form
+                self._w_in_nk = torch.cat([w1, w2], dim=0).contiguous()             # (2D, d_model): nn.Linear form
             self._w_in_key = key
         Bp, L, dm = x.shape
-        x2 = x.reshape(1, Bp * L, dm).expand(2, Bp * L, dm)
-        xz = torch.bmm(x2, self._w_in)                                               # (2, B'L, D)
+        D = self.d_inner
+        if self._tc_ok(x) and x.is_contiguous():
+            xz = torch.empty((2, Bp * L, D), dtype=x.dtype, device=x.device)
+            a = x.view(Bp * L, dm)
+            if D % 32 == 0:
+                gemm.run([gemm.Problem(a, self._w_in_nk, xz, planes=2)], name="gemm_inproj")
+            else:          # a column tile may not straddle the two planes: two problems of one launch
+                gemm.run([gemm.Problem(a, w1, xz[0]), gemm.Problem(a, w2, xz[1])], name="gemm_inproj")
+        else:
+            x2 = x.reshape(1, Bp * L, dm).expand(2, Bp * L, dm)
+            xz = torch.bmm(x2, self._w_in)                                           # (2, B'L, D)
         return xz[0].view(Bp, L, -1), xz[1].view(Bp, L, -1)
 
     def _check_forward_only(self, x):

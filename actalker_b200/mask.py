@@ -51,7 +51,7 @@ def mask_to_index(mask: torch.Tensor, num_queries: int) -> torch.Tensor:
 
 @dataclass
 class MaskIndex:
-    idx: torch.Tensor        # (n_sel,) int32, ascending, on the mask's device — what the kernels read
+    idx: torch.Tensor        # (n_sel,) int32, ascending, on the LAYER's device — what the kernels read
     idx64: torch.Tensor      # (n_sel,) int64 — for torch-side gathers of the small x_dbl rows
     selected: torch.Tensor   # (L,) uint8 row flags for the merge kernel
     n_sel: int               # host copy (one sync when the entry is created)
@@ -72,11 +72,18 @@ class MaskIndexCache:
         self._max = max_entries
         self.misses = 0
 
-    def get(self, mask: torch.Tensor, L: int) -> MaskIndex:
-        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, str(mask.device), L)
+    def get(self, mask: torch.Tensor, L: int, device=None) -> MaskIndex:
+        """`device`: where the kernels will read the index list (the activations' device).  The downsample itself runs
+        where the reference runs it — on the mask's own device, in the mask's dtype — and only its integer results are
+        moved, as the reference's `xz[:, idx, :]` does implicitly when the mask lives on the CPU or on another GPU.
+        Handing a host pointer to the kernels instead would fault the context (no Python exception)."""
+        device = mask.device if device is None else torch.device(device)
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, str(mask.device), L, str(device))
         hit = self._entries.get(key)
         if hit is not None:
             return hit
+        if mask.dim() != 4:
+            raise RuntimeError(f"mask must be (b, 1, H, W) as pipeline ...two_ip.py:632-633 builds it, got {tuple(mask.shape)}")
         self.misses += 1
         down = downsample(mask[:, 0, :, :], mask.shape[0], L, 1)     # (b, L, 1), the reference's own expression
         idx64 = down.view(-1).int().nonzero().view(-1)
@@ -84,10 +91,11 @@ class MaskIndexCache:
             # masks with batch > 1 flatten to b*L entries upstream and then index out of range (:1963);
             # the live pipeline always passes batch 1 (pipeline ...two_ip.py:632-633).
             raise RuntimeError(f"mask of shape {tuple(mask.shape)} selects token {int(idx64[-1])} >= L={L}")
-        sel = torch.zeros(L, dtype=torch.uint8, device=mask.device)
+        idx64 = idx64.to(device)
+        sel = torch.zeros(L, dtype=torch.uint8, device=device)
         sel[idx64] = 1
         entry = MaskIndex(idx=idx64.to(torch.int32), idx64=idx64, selected=sel, n_sel=int(idx64.numel()), L=L,
-                          mask_ref=mask, weight=down[0, :, 0].contiguous())
+                          mask_ref=mask, weight=down[0, :, 0].contiguous().to(device))
         if len(self._entries) >= self._max:
             self._entries.pop(next(iter(self._entries)))
         self._entries[key] = entry

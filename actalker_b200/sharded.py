@@ -173,12 +173,12 @@ class ShardedSS2DCondV10(torch.nn.Module):
             with _timed("all_gather", x.device):
                 self._peer.fence()
             y = self.gathered_layernorm(mine, (self.world, Bp, L, Ds), xz1.dtype, x.device)
-            return layer.out_proj(y)
+            return layer._out_proj(y)
         else:
             merged = layer.scan_core(xz1, xz2, tail1, tail2, m1, m2, ch_slice=(lo, hi))  # (B', L, Ds)
             with _timed("all_gather", x.device):
                 gathered = all_gather_slices(merged, self.group)                           # (P, B', L, Ds)
-        return layer.out_proj(self.gathered_layernorm(gathered))
+        return layer._out_proj(self.gathered_layernorm(gathered))
 
     def gathered_layernorm(self, gathered, shape=None, dtype=None, device=None) -> torch.Tensor:
         """LayerNorm over the gathered (rank, row, slice) layout: `gathered` is a (P, B', L, Ds) tensor, or the raw

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 9
+#define ACTK_ABI_VERSION 10
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -142,7 +142,7 @@ typedef struct {
   /* Fused dt_proj (mamba_layer.py:1523).  0: the caller supplies delta / delta_tail.
    * 32 / 48 / 80 (f16 / bf16 only): xdbl / xdbl_tail hold, after the 4*N B|C columns, the dt_proj INPUT of
    * direction k in columns [4N + k*dt_rank_pad, 4N + (k+1)*dt_rank_pad) (rank zero-padded), and the kernel
-   * computes delta = dt_in @ w_dt[k]^T per 16-token tile with mma.sync (fp32 accumulate, one rounding to `dtype`,
+   * computes delta = dt_in @ w_dt[k]^T per 16-token tile with tcgen05.mma (fp32 accumulate, one rounding to `dtype`,
    * the rounding point of the reference's dts tensor).  Removes the delta tensors' HBM round trip. */
   int dt_rank_pad;
 } actk_masked_scan_args;
@@ -207,6 +207,33 @@ int actk_merge_ln_outproj_fwd(const actk_merge_ln_args *args, const void *w_out,
  *      parts*Ds channels (mamba_layer.py:1984 needs complete channels).  Ds % 8 == 0, parts*Ds <= 8192. */
 int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int Ds, const void *gamma, const void *beta,
                                 float eps, void *out, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3c) The layer's dense projections on the tensor cores: C = epilogue(A @ W^T) for up to
+ *      ACTK_GEMM_MAX_PROBLEMS independent products per launch (both branches, latent + tail tokens).
+ *      Replaces the reference's nn.Linear / einsum calls of mamba_layer.py:1960-1961, :1966, :1972, :1977
+ *      (in_proj1/2, id/audio/exp projections), :1521 (x_proj), :1523 (dt_proj) and :1985 (out_proj) on the 16-bit
+ *      route: fp32 accumulation, one rounding to `dtype`.  Persistent TMA + tcgen05.mma + tensor-memory kernel.
+ *   a : (M, K) row pitch lda        activations, `dtype`
+ *   w : (N, K) row pitch ldw        weight as nn.Linear stores it (out_features, in_features)
+ *   c : (M, N) row pitch ldc        or, with planes > 1, `planes` tensors of (M, N / planes) that are plane_stride
+ *                                   elements apart (in_proj1 | in_proj2 from one stacked weight: x is read once)
+ *   pitches in ELEMENTS and multiples of 8 (16 bytes); pointers 16-byte aligned; any M, N, K > 0.
+ *   epilogue ACTK_GEMM_EPI_SILU: c = round(silu(round(a @ w^T))), the act(Linear(.)) of the condition tokens.
+ *   dtype: ACTK_F16 / ACTK_BF16 (fp32 activations keep the caller's fp32 GEMM; ACTK_ERR_BAD_DTYPE).
+ * ------------------------------------------------------------------------------------------- */
+#define ACTK_GEMM_MAX_PROBLEMS 4
+#define ACTK_GEMM_EPI_NONE 0
+#define ACTK_GEMM_EPI_SILU 1
+typedef struct {
+  const void *a, *w;
+  void *c;
+  long long lda, ldw, ldc, plane_stride;
+  int M, N, K, planes;
+} actk_gemm_problem;
+
+int actk_gemm_tn_supported(const actk_gemm_problem *problem, int dtype); /* 1 if the shape / alignment rules hold */
+int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, int epilogue, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) A-structure probe.  Writes *flag_dev = ACTK_A_POWER if |A[d][n] - (n+1)*A[d][0]| <=
