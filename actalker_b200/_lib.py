@@ -59,7 +59,7 @@ class MergeLnArgs(C.Structure):
 
 class GemmProblem(C.Structure):
     _fields_ = [("a", _vp), ("w", _vp), ("c", _vp), ("lda", _ll), ("ldw", _ll), ("ldc", _ll), ("plane_stride", _ll),
-                ("M", _i), ("N", _i), ("K", _i), ("planes", _i)]
+                ("M", _i), ("N", _i), ("K", _i), ("planes", _i), ("epilogue", _i)]
 
 
 GEMM_MAX_PROBLEMS = 4
@@ -126,7 +126,7 @@ def load():
         getattr(lib, name).restype = _i
     lib.actk_gemm_tn_supported.argtypes = [C.POINTER(GemmProblem), _i]
     lib.actk_gemm_tn_supported.restype = _i
-    lib.actk_gemm_tn_fwd.argtypes = [C.POINTER(GemmProblem), _i, _i, _i, _vp]
+    lib.actk_gemm_tn_fwd.argtypes = [C.POINTER(GemmProblem), _i, _i, _vp]
     lib.actk_gemm_tn_fwd.restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll

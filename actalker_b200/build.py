@@ -49,7 +49,7 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, out: str = None, defs=()) -> str:
-    """Build the library.  `out`/`defs` produce a tuning variant (e.g. defs=["ACTK_POLY_PAIRS=3"]) beside the
+    """Build the library.  `out`/`defs` produce a tuning variant (e.g. defs=["ACTK_POLY_STATES=3"]) beside the
     default one; select it at run time with ACTK_LIB_PATH."""
     variant = out is not None
     out = out or LIB_PATH

@@ -150,6 +150,22 @@ __device__ __forceinline__ uint64_t ex2_poly2(uint64_t t2) {
             __int_as_float(__float_as_int(ph) + (__float_as_int(sh) << 23)));
 }
 
+// Scalar form of ex2_poly2 for ONE value (same split, same polynomial): 11 issue slots instead of one MUFU.  With the
+// MUFU pipe at 8 cycles per warp instruction and the issue port at ~1.1 per scalar / 2.3 per packed instruction, moving an
+// odd number of the 16 per-step exponentials lets the two limits meet (scan_core.cuh, ACTK_POLY_STATES).
+__device__ __forceinline__ float ex2_poly1(float t) {
+  t = fmaxf(t, -126.0f);
+  const float s = t + 12582912.0f;
+  const float f = t - (s - 12582912.0f);
+  float p = 0.001326472731307149f;
+  p = fmaf(p, f, 0.009671512991189957f);
+  p = fmaf(p, f, 0.05550733581185341f);
+  p = fmaf(p, f, 0.24022242426872253f);
+  p = fmaf(p, f, 0.6931470036506653f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(s) << 23));
+}
+
 // ----------------------------------------------------------------------------- mbarrier / TMA bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -16,9 +16,13 @@
 //     warp 0     TMA producer: A (128 x 64) and W (BN x 64) slabs, SWIZZLE_128B, into a 4-6 deep shared-memory ring
 //     warp 1     one thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 16; SASS UTCHMMA) into one of TWO
 //                accumulator buffers in tensor memory (2 x 256 columns) and commits to the ring's / buffer's mbarriers
-//     warps 2-9  epilogue: tcgen05.ld (LDTM) of 32-column chunks (lane = row), rounding (+ SiLU), 16-byte stores into a
-//                64-byte-swizzled staging tile, TMA store (UTMASTG) of 32 x 32 boxes; the accumulator buffer is released
-//                as soon as it has been read, so tile i+1's MMAs run under tile i's stores
+//     warps 2-9  epilogue, 64 output columns at a time: every warp reads 32 columns of its 32 rows from tensor memory
+//                (tcgen05.ld / LDTM, lane = row), rounds (+ SiLU) and writes 16-byte pieces into a 128 x 64 staging tile
+//                in the 128-byte-swizzled layout; one thread sends the tile with ONE TMA store (UTMASTG, 16 KB, full
+//                128-byte lines); three staging tiles rotate so stores stay in flight (first version: one 32 x 32 box
+//                per warp and chunk = 8x as many 2 KB stores of half lines: dt_proj 229 us against 125 us for cuBLAS).
+//                The accumulator buffer is released as soon as it has been read, so tile i+1's MMAs run under tile
+//                i's stores
 // Up to 4 independent problems per launch (both branches, latent + tail tokens) share one grid through a tile table.
 // Tails of M / N / K need no special code: TMA zero-fills loads and clips stores at the tensor bounds.
 #include <cuda.h>
@@ -33,17 +37,22 @@ constexpr int kBM = 128;               // rows per tile == MMA M
 constexpr int kBK = 64;                // K elements per slab: 128-byte rows, one SWIZZLE_128B atom wide
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kABytes = kBM * kBK * 2;
-constexpr uint32_t kEpiBytes = kEpiWarps * 2 * 2048;   // per warp: two 32 x 32 staging tiles of 16-bit elements
+constexpr int kEpiBufs = 3;
+constexpr uint32_t kEpiBufBytes = kBM * 64 * 2;        // one staging tile: 128 rows x 64 columns of 16-bit elements
+constexpr uint32_t kEpiBytes = kEpiBufs * kEpiBufBytes;
 constexpr int kMaxGemmProblems = ACTK_GEMM_MAX_PROBLEMS;
 
 struct GemmProblemDev {
-  CUtensorMap a, w, c;
+  CUtensorMap a, w, c;   // c: 64-column store boxes (SWIZZLE_128B)
+  CUtensorMap c32;       // 32-column store boxes (SWIZZLE_64B) for the last chunk of a tile whose width is 32 mod 64
+  int tiles_per_plane;
   int n_tiles;        // column tiles per row tile
   int k_slabs;
   int bn;             // columns per tile (multiple of 32, <= 256)
   int tile_begin;     // index of this problem's first tile in the launch's tile table
   int plane_cols;     // output columns per plane (N when the output is one tensor)
   int M, N;
+  int epilogue;       // ACTK_GEMM_EPI_* of this problem
 };
 struct alignas(64) GemmParams {
   GemmProblemDev p[kMaxGemmProblems];
@@ -124,7 +133,7 @@ __device__ __forceinline__ int gemm_problem_of(const GemmParams &P, int t) {
   return g;
 }
 
-template <typename T>
+template <typename T, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t gemm_smem[];
   const uint32_t base = (smem_u32(gemm_smem) + 1023u) & ~1023u;     // SWIZZLE_128B atoms want 1024-byte alignment
@@ -140,7 +149,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     for (int s = 0; s < S; ++s) { gemm_bar_init(full_bar + 8 * s, 1); gemm_bar_init(empty_bar + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { gemm_bar_init(tfull_bar + 8 * b, 1); gemm_bar_init(tempty_bar + 8 * b, kEpiWarps); }
     mbar_fence_init();
-    for (int g = 0; g < P.n_problems; ++g) { tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); }
+    for (int g = 0; g < P.n_problems; ++g) {
+      tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); tmap_prefetch(&P.p[g].c32);
+    }
   }
   __syncwarp();
   if (warp == 1) {   // 2 accumulator buffers x 256 columns
@@ -199,49 +210,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
   } else {             // ---------------------------------------------------------------- epilogue warps
     const int ew = warp - 2;
     const int q = warp & 3;                  // tensor-memory lane quadrant this warp may read: warp id % 4
-    const int h = ew >> 2;                   // which half of the 32-column chunks
-    const uint32_t stage0 = epi_base + (uint32_t)ew * 4096;
+    const int h = ew >> 2;                   // which 32 of a chunk's 64 columns
+    const int r = q * 32 + lane;             // row of the tile this thread converts
+    const bool leader = ew == 0 && lane == 0;
     uint32_t tc = 0, chunk_count = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
       const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
       const int local = tile - pr.tile_begin;
       const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
+      const int plane = n / pr.tiles_per_plane;
+      const int col0 = (n - plane * pr.tiles_per_plane) * pr.bn;     // first column of the tile within its plane
       const uint32_t b = tc & 1, ub = tc >> 1;
       gemm_bar_wait(tfull_bar + 8 * b, ub & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row0 = m * kBM + q * 32;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256;
-      for (int c = h; c < pr.bn / 32; c += 2) {
-        const int col = n * pr.bn + c * 32;
-        uint32_t r[32];
-        gemm_tmem_ld16(trow + c * 32, r);
-        gemm_tmem_ld16(trow + c * 32 + 16, r + 16);
-        gemm_tmem_wait32(r);
-        if (col >= pr.N || row0 >= pr.M) continue;          // nothing of this chunk lies inside the output
-        uint4 v[4];
-        T *e = reinterpret_cast<T *>(v);
+      const int nchunks = (pr.bn + 63) >> 6;
+      for (int cc = 0; cc < nchunks; ++cc, ++chunk_count) {
+        const int width = pr.bn - cc * 64 >= 64 ? 64 : 32;          // bn is a multiple of 32
+        const uint32_t buf = epi_base + (chunk_count % kEpiBufs) * kEpiBufBytes;
+        if (h * 32 < width) {
+          uint32_t v32[32];
+          gemm_tmem_ld16(trow + cc * 64 + h * 32, v32);
+          gemm_tmem_ld16(trow + cc * 64 + h * 32 + 16, v32 + 16);
+          gemm_tmem_wait32(v32);
+          // act(Linear(x)): the product is a `dtype` tensor first.  EPI says whether ANY problem of the launch wants it
+          // (compile-time: launches without SiLU carry no trace of it), the problem's own flag decides per tile
+          if (EPI == ACTK_GEMM_EPI_SILU && pr.epilogue == ACTK_GEMM_EPI_SILU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float f = __uint_as_float(r[i]);
-          if (P.epilogue == ACTK_GEMM_EPI_SILU) f = silu(IO<T>::rnd(f));   // act(Linear(x)): the product is a `dtype` tensor first
-          IO<T>::st(e + i, f);
-        }
-        const uint32_t buf = stage0 + (chunk_count & 1) * 2048;
-        ++chunk_count;
-        if (lane == 0) bulk_wait_read<1>();                  // the store issued from this buffer two chunks ago has read it
-        __syncwarp();
-        // staging tile: 32 rows x 64 bytes, SWIZZLE_64B (16-byte piece j of row r at (j ^ ((r >> 1) & 3)))
+            for (int i = 0; i < 32; ++i) v32[i] = __float_as_uint(silu(IO<T>::rnd(__uint_as_float(v32[i]))));
+          }
+          uint4 v[4];
+          T *e = reinterpret_cast<T *>(v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t addr = buf + (uint32_t)lane * 64 + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w)
-                       : "memory");
+          for (int i = 0; i < 32; ++i) IO<T>::st(e + i, __uint_as_float(v32[i]));
+          // staging tile, row r: 64 columns = 128 bytes in the SWIZZLE_128B pattern (16-byte piece j at j ^ (r & 7)),
+          // or, for a 32-column last chunk, 64 bytes in the SWIZZLE_64B pattern (piece j at j ^ ((r >> 1) & 3))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = width == 64 ? buf + (uint32_t)r * 128 + (uint32_t)(((4 * h + j) ^ (r & 7)) << 4)
+                                              : buf + (uint32_t)r * 64 + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w)
+                         : "memory");
+          }
+          fence_proxy_async();
         }
-        fence_proxy_async();
+        // the leader makes sure the staging tile of the NEXT chunk is free (its store, three chunks back, has read it)
+        // before anyone passes the barrier, then sends this chunk: one barrier per chunk
+        if (leader) bulk_wait_read<kEpiBufs - 2>();
         __syncwarp();
-        if (lane == 0) {
-          const int plane = col / pr.plane_cols;
-          gemm_tma_store_3d(&pr.c, col - plane * pr.plane_cols, row0, plane, buf);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (leader && col0 + cc * 64 < pr.plane_cols) {
+          gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, m * kBM, plane, buf);
           bulk_commit();
         }
       }
@@ -249,7 +268,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) gemm_bar_arrive(tempty_bar + 8 * b);    // this warp's reads of the buffer are done
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -304,13 +323,16 @@ static const char *gemm_check(const actk_gemm_problem &p, int es) {
 }
 
 template <typename T>
-static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, int epilogue, cudaStream_t stream) {
+static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream_t stream) {
   GemmEncodeFn fn = gemm_encode_fn();
   if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
   const CUtensorMapDataType dt = dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   GemmParams P;
   memset(&P, 0, sizeof(P));
   P.n_problems = n;
+  int epilogue = ACTK_GEMM_EPI_NONE;
+  for (int g = 0; g < n; ++g)
+    if (pr[g].epilogue == ACTK_GEMM_EPI_SILU) epilogue = ACTK_GEMM_EPI_SILU;
   P.epilogue = epilogue;
   int tiles = 0, bn_max = 32;
   for (int g = 0; g < n; ++g) {
@@ -320,8 +342,10 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, int epilog
     d.bn = gemm_pick_bn(p.N, pc);
     d.plane_cols = pc;
     d.M = p.M; d.N = p.N;
+    d.epilogue = p.epilogue;
     d.k_slabs = (p.K + kBK - 1) / kBK;
-    d.n_tiles = p.planes * ((pc + d.bn - 1) / d.bn);
+    d.tiles_per_plane = (pc + d.bn - 1) / d.bn;
+    d.n_tiles = p.planes * d.tiles_per_plane;
     d.tile_begin = tiles;
     tiles += ((p.M + kBM - 1) / kBM) * d.n_tiles;
     bn_max = d.bn > bn_max ? d.bn : bn_max;
@@ -342,13 +366,14 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, int epilog
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (W of problem %d) failed with CUresult %d", g, (int)r);
     }
-    {   // C (plane_cols, M, planes): the epilogue stores 32 x 32 boxes
+    for (int narrow = 0; narrow < 2; ++narrow) {   // C (plane_cols, M, planes): 128-row store boxes of 64 / 32 columns
       cuuint64_t dims[3] = {(cuuint64_t)pc, (cuuint64_t)p.M, (cuuint64_t)p.planes};
       cuuint64_t strides[2] = {(cuuint64_t)p.ldc * sizeof(T),
                                (cuuint64_t)(p.planes > 1 ? p.plane_stride : (long long)p.ldc * p.M) * sizeof(T)};
-      cuuint32_t box[3] = {32, 32, 1};
-      CUresult r = fn(&d.c, dt, 3, p.c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      cuuint32_t box[3] = {narrow ? 32u : 64u, (cuuint32_t)kBM, 1};
+      CUresult r = fn(narrow ? &d.c32 : &d.c, dt, 3, p.c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (C of problem %d) failed with CUresult %d", g, (int)r);
     }
   }
@@ -364,11 +389,12 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, int epilog
   if (stages < 2) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: %d bytes of shared memory per block do not hold two pipeline stages", smem_max);
   P.stages = stages;
   const size_t smem = 1024 + (size_t)stages * P.stage_bytes + kEpiBytes + 16 * (size_t)stages + 64;
-  auto kern = gemm_tn_kernel<T>;
-  static int configured[64] = {};   // per device: the largest dynamic shared memory size requested so far
-  if (dev < 64 && configured[dev] < (int)smem) {
+  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE>;
+  static int configured[64][2] = {};   // per device and epilogue: dynamic shared memory limit raised
+  const int ei = epilogue == ACTK_GEMM_EPI_SILU ? 1 : 0;
+  if (dev < 64 && !configured[dev][ei]) {
     ACTK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    configured[dev] = smem_max;
+    configured[dev][ei] = 1;
   }
   kern<<<tiles < sms ? tiles : sms, kGemmThreads, smem, stream>>>(P);
   ACTK_CUDA_OK(cudaGetLastError());
@@ -384,17 +410,18 @@ extern "C" int actk_gemm_tn_supported(const actk_gemm_problem *p, int dtype) {
   return gemm_check(*p, 2) == nullptr;
 }
 
-extern "C" int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, int epilogue, void *stream) {
+extern "C" int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, void *stream) {
   if (!problems) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: problems is NULL");
   if (n_problems < 1 || n_problems > kMaxGemmProblems)
     ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: n_problems=%d (1..%d per launch)", n_problems, kMaxGemmProblems);
   if (dtype != ACTK_F16 && dtype != ACTK_BF16)
     ACTK_FAIL(ACTK_ERR_BAD_DTYPE, "gemm_tn: dtype=%d (the tensor-core route is f16 / bf16; fp32 projections stay with the caller)", dtype);
-  if (epilogue != ACTK_GEMM_EPI_NONE && epilogue != ACTK_GEMM_EPI_SILU) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: epilogue=%d", epilogue);
   for (int g = 0; g < n_problems; ++g) {
-    const char *why = gemm_check(problems[g], 2);
+    const actk_gemm_problem &p = problems[g];
+    if (p.epilogue != ACTK_GEMM_EPI_NONE && p.epilogue != ACTK_GEMM_EPI_SILU)
+      ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: problem %d: epilogue=%d", g, p.epilogue);
+    const char *why = gemm_check(p, 2);
     if (why) {
-      const actk_gemm_problem &p = problems[g];
       const bool align = strstr(why, "16 bytes") != nullptr;
       ACTK_FAIL(align ? ACTK_ERR_BAD_ALIGN : (strstr(why, "NULL") ? ACTK_ERR_BAD_ARG : ACTK_ERR_BAD_SHAPE),
                 "gemm_tn: problem %d (M=%d N=%d K=%d lda=%lld ldw=%lld ldc=%lld planes=%d): %s", g, p.M, p.N, p.K, p.lda, p.ldw,
@@ -402,6 +429,6 @@ extern "C" int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problem
     }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == ACTK_F16) return launch_gemm<__half>(problems, n_problems, dtype, epilogue, st);
-  return launch_gemm<__nv_bfloat16>(problems, n_problems, dtype, epilogue, st);
+  if (dtype == ACTK_F16) return launch_gemm<__half>(problems, n_problems, dtype, st);
+  return launch_gemm<__nv_bfloat16>(problems, n_problems, dtype, st);
 }

@@ -23,11 +23,14 @@
 
 namespace actk {
 
-#ifndef ACTK_POLY_PAIRS
-#define ACTK_POLY_PAIRS 1   // state pairs per step whose exp runs on the FMA pipe (general-A path); tuned on B200 at
-                            // config 2 with chain mode: 0 -> 1.53 ms, 1 -> 1.50 ms, 2 -> 1.59 ms, 3 -> 1.73 ms
+#ifndef ACTK_POLY_STATES
+#define ACTK_POLY_STATES 2  // states per step whose exp runs on the FMA pipe instead of the MUFU unit (general-A path);
+                            // round 1, whole pairs on B200 at config 2 with chain mode: 0 -> 1.53 ms, 2 -> 1.50 ms,
+                            // 4 -> 1.59 ms, 6 -> 1.73 ms.  Odd counts take the scalar polynomial for one state.
 #endif
-constexpr int kPolyPairs = ACTK_POLY_PAIRS;
+constexpr int kPolyStates = ACTK_POLY_STATES;
+constexpr int kPolyPairs = kPolyStates / 2;     // whole pairs: packed polynomial
+constexpr bool kPolyOdd = (kPolyStates & 1) != 0;  // plus one state of the next pair: scalar polynomial
 
 struct StepIn {
   float dt, x, u;
@@ -85,6 +88,10 @@ struct ChannelScan {
         const uint64_t t2 = mul2(d2, a2[j]);
         if (j >= kN / 2 - kPolyPairs) {
           p[j] = ex2_poly2(t2);
+        } else if (kPolyOdd && j == kN / 2 - kPolyPairs - 1) {
+          float lo, hi;
+          upk(t2, lo, hi);
+          p[j] = pk(ex2(lo), ex2_poly1(hi));
         } else {
           float lo, hi;
           upk(t2, lo, hi);

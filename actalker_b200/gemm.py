@@ -24,10 +24,10 @@ class Problem:
     """C = A @ W^T.  a: (M, K) view with unit column stride; w: (N, K) with unit column stride;
     out: (M, N) view with unit column stride, or (planes, M, N / planes) contiguous planes."""
 
-    __slots__ = ("a", "w", "out", "planes")
+    __slots__ = ("a", "w", "out", "planes", "silu")
 
-    def __init__(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, planes: int = 1):
-        self.a, self.w, self.out, self.planes = a, w, out, planes
+    def __init__(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, planes: int = 1, silu: bool = False):
+        self.a, self.w, self.out, self.planes, self.silu = a, w, out, planes, silu
 
     def fill(self, p: "_lib.GemmProblem"):
         a, w, out = self.a, self.w, self.out
@@ -50,6 +50,7 @@ class Problem:
         p.ldc = ldc if M > 1 else N // self.planes
         p.plane_stride = plane_stride
         p.M, p.N, p.K, p.planes = M, N, K, self.planes
+        p.epilogue = _lib.GEMM_EPI_SILU if self.silu else _lib.GEMM_EPI_NONE
 
 
 def usable(*tensors: Optional[torch.Tensor]) -> bool:
@@ -59,7 +60,8 @@ def usable(*tensors: Optional[torch.Tensor]) -> bool:
 
 
 def run(problems: Sequence[Problem], silu: bool = False, name: str = "gemm"):
-    """Launch the problems (groups of up to four per launch) on the current stream of their device."""
+    """Launch the problems (groups of up to four per launch) on the current stream of their device.
+    silu=True sets the SiLU epilogue on every problem (a Problem can also carry its own flag)."""
     from .mamba_layer import _timed   # timing hook shared with the other C-ABI launches
     lib = _lib.load()
     problems = [p for p in problems if p.a.shape[0] > 0]
@@ -67,7 +69,9 @@ def run(problems: Sequence[Problem], silu: bool = False, name: str = "gemm"):
         return
     dev = problems[0].a.device
     dtype = _DTYPES[problems[0].a.dtype]
-    epi = _lib.GEMM_EPI_SILU if silu else _lib.GEMM_EPI_NONE
+    if silu:
+        for p in problems:
+            p.silu = True
     stream = ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     for i in range(0, len(problems), _lib.GEMM_MAX_PROBLEMS):
         group = problems[i:i + _lib.GEMM_MAX_PROBLEMS]
@@ -75,18 +79,27 @@ def run(problems: Sequence[Problem], silu: bool = False, name: str = "gemm"):
         for p, slot in zip(group, arr):
             p.fill(slot)
         with torch.cuda.device(dev), _timed(name, dev):
-            _lib.check(lib.actk_gemm_tn_fwd(arr, len(group), dtype, epi, stream), "actk_gemm_tn_fwd")
+            _lib.check(lib.actk_gemm_tn_fwd(arr, len(group), dtype, stream), "actk_gemm_tn_fwd")
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, silu: bool = False, name: str = "gemm") -> torch.Tensor:
-    """nn.Linear(bias=False) [+ SiLU] on (..., K) activations: this repo's kernel for 16-bit CUDA tensors, torch otherwise."""
-    if usable(x, w) and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
+def linear(x: torch.Tensor, w: torch.Tensor, silu: bool = False, name: str = "gemm", out: torch.Tensor = None) -> torch.Tensor:
+    """nn.Linear(bias=False) [+ SiLU] on (..., K) activations: this repo's kernel for 16-bit CUDA tensors, torch otherwise.
+    out: optional contiguous (..., N) destination of x's dtype."""
+    shape = (*x.shape[:-1], w.shape[0])
+    if out is not None and (tuple(out.shape) != shape or not out.is_contiguous() or out.dtype != x.dtype):
+        raise RuntimeError(f"gemm.linear: out {tuple(out.shape)} {out.dtype} must be contiguous {shape} {x.dtype}")
+    if usable(x, w) and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 and (out is None or out.data_ptr() % 16 == 0):
         a = x.reshape(-1, x.shape[-1])
         if a.stride(1) != 1 or a.stride(0) % 8 or a.data_ptr() % 16:
             a = a.contiguous()
         wc = w if (w.stride(1) == 1 and w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0) else w.contiguous()
-        out = torch.empty((a.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
-        run([Problem(a, wc, out)], silu=silu, name=name)
-        return out.view(*x.shape[:-1], w.shape[0])
+        if out is None:
+            out = torch.empty(shape, dtype=x.dtype, device=x.device)
+        run([Problem(a, wc, out.view(a.shape[0], w.shape[0]))], silu=silu, name=name)
+        return out
     y = torch.nn.functional.linear(x, w.to(x.dtype))
-    return torch.nn.functional.silu(y) if silu else y
+    y = torch.nn.functional.silu(y) if silu else y
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y

@@ -477,7 +477,7 @@ class SS2D_cond_v10(nn.Module):
         self.mask_cache = MaskIndexCache()
 
     def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None, weights=None,
-                  layernorm=None, out_proj=False, push=None):
+                  layernorm=None, out_proj=False, push=None, out_buf=None):
         """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
         ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
         ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
@@ -520,14 +520,19 @@ class SS2D_cond_v10(nn.Module):
             return y
         with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
-        return self._out_proj(out) if out_proj else out
+        return self._out_proj(out, out=out_buf) if out_proj else out
 
-    def _out_proj(self, y):
-        """out_proj (mamba_layer.py:1985): tensor-core kernel for 16-bit activations, torch otherwise."""
+    def _out_proj(self, y, out=None):
+        """out_proj (mamba_layer.py:1985): tensor-core kernel for 16-bit activations, torch otherwise.
+        out: optional (B', L, d_model) contiguous destination (a slot of a multi-GPU gather buffer)."""
         w = self.out_proj.weight
         if TC_GEMM and self.out_proj.bias is None and gemm.usable(y, w) and y.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
-            return gemm.linear(y, w, name="gemm_outproj")
-        return self.out_proj(y)
+            return gemm.linear(y, w, name="gemm_outproj", out=out)
+        res = self.out_proj(y)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
     use_id = True   # SS2D_cond_v10_wo_id drops the identity token (and has no id_proj)
 
@@ -541,6 +546,27 @@ class SS2D_cond_v10(nn.Module):
         # too: indexing moves the index tensor); the downsample itself runs on the mask's own device and dtype
         m1 = self.mask_cache.get(masks[0], L, device=x.device)
         m2 = self.mask_cache.get(masks[1], L, device=x.device)
+        Bp, n_c, dc = conds.shape
+        D = self.d_inner
+        if (self.use_id and n_c >= 2 and BATCH_IN_PROJ and self._tc_ok(x, id_emb, conds) and conds.is_contiguous()
+                and x.is_contiguous()):
+            # Tensor-core route, two launches on the current stream, no glue kernels:
+            #   (1) audio_proj over ALL rows of `conds` + SiLU, stored one row further down in tail1, and exp_proj of the
+            #       last token of every frame into slot 1 of tail2.  `conds` holds 32 audio tokens then the expression
+            #       token per frame, tail1 the id token then the 32 audio tokens: the shift puts every audio token in
+            #       place, and the rows it also fills with the (meaningless) audio projection of the expression token
+            #       are exactly the id slots, which launch (2) overwrites;
+            #   (2) in_proj1 | in_proj2 (x read once, two output planes) together with id_proj + SiLU into slot 0 of
+            #       both tails.
+            tail1 = torch.empty((Bp, n_c, D), dtype=x.dtype, device=x.device)
+            tail2 = torch.empty((Bp, 2, D), dtype=x.dtype, device=x.device)
+            gemm.run([gemm.Problem(conds.view(Bp * n_c, dc)[:-1], self.audio_proj.weight, tail1.view(Bp * n_c, D)[1:]),
+                      gemm.Problem(conds[:, -1, :], self.exp_proj.weight, tail2[:, 1, :])], silu=True, name="gemm_cond")
+            idm = id_emb.reshape(Bp, dc)
+            ids = [gemm.Problem(idm, self.id_proj.weight, tail1[:, 0, :], silu=True),
+                   gemm.Problem(idm, self.id_proj.weight, tail2[:, 0, :], silu=True)]
+            xz1, xz2 = self._in_proj_both(x, extra=ids)
+            return xz1, xz2, tail1, tail2, m1, m2
         fork = _Fork(x.device)
         with fork:                                   # 35 id / condition tokens per frame: side stream
             tail1, tail2 = self._tail_tokens(id_emb, conds)
@@ -559,25 +585,9 @@ class SS2D_cond_v10(nn.Module):
 
     def _tail_tokens(self, id_emb, conds):
         """tail1 = [SiLU(id_proj(id)), SiLU(audio_proj(audio tokens))], tail2 = [SiLU(id_proj(id)), SiLU(exp_proj(exp token))]
-        (mamba_layer.py:1958-1960, 1966, 1977).  Tensor-core route: the products are written straight into the two tail
-        buffers — `conds` holds 32 audio tokens then the expression token per frame, tail1 the id token then the 32 audio
-        tokens, so audio_proj over ALL rows of `conds`, stored one row further down, puts every audio token in place; the
-        rows it also fills with the (meaningless) audio projection of the expression token are exactly the id slots,
-        which the id_proj launch that follows overwrites."""
-        Bp, n_c, dc = conds.shape
-        D = self.d_inner
-        if self.use_id and n_c >= 2 and self._tc_ok(id_emb, conds) and conds.is_contiguous():
-            tail1 = torch.empty((Bp, n_c, D), dtype=conds.dtype, device=conds.device)
-            tail2 = torch.empty((Bp, 2, D), dtype=conds.dtype, device=conds.device)
-            flat = conds.view(Bp * n_c, dc)
-            gemm.run([gemm.Problem(flat[:-1], self.audio_proj.weight, tail1.view(Bp * n_c, D)[1:]),
-                      gemm.Problem(conds[:, -1, :], self.exp_proj.weight, tail2[:, 1, :])], silu=True, name="gemm_cond")
-            idm = id_emb.reshape(Bp, dc)
-            gemm.run([gemm.Problem(idm, self.id_proj.weight, tail1[:, 0, :]),
-                      gemm.Problem(idm, self.id_proj.weight, tail2[:, 0, :])], silu=True, name="gemm_cond")
-            return tail1, tail2
+        (mamba_layer.py:1958-1960, 1966, 1977) — the route for fp32 activations and for the variant without an id token."""
         audio_cond, exp_cond = conds[:, :-1], conds[:, -1:]
-        if not self.use_id and self._tc_ok(conds):           # v10_wo_id: no id slot to absorb the shifted store
+        if not self.use_id and self._tc_ok(conds):           # v10_wo_id: no id slot to absorb a shifted store
             return (gemm.linear(audio_cond, self.audio_proj.weight, silu=True, name="gemm_cond"),
                     gemm.linear(exp_cond, self.exp_proj.weight, silu=True, name="gemm_cond"))
         tail1, tail2 = self.act1(self.audio_proj(audio_cond)), self.act2(self.exp_proj(exp_cond))
@@ -586,7 +596,7 @@ class SS2D_cond_v10(nn.Module):
             tail1, tail2 = torch.cat([id_tok, tail1], dim=1), torch.cat([id_tok, tail2], dim=1)
         return tail1.contiguous(), tail2.contiguous()
 
-    def _in_proj_both(self, x):
+    def _in_proj_both(self, x, extra=()):
         """in_proj1(x), in_proj2(x) (mamba_layer.py:1960-1961) as ONE product: the two weights stacked to (2D, d_model),
         the two results written as separate contiguous planes — x is read once per call instead of once per branch.
         Tensor-core route (16-bit): one actk_gemm_tn_fwd launch; fp32: one batched torch GEMM over a stride-0 batch."""
@@ -606,10 +616,11 @@ class SS2D_cond_v10(nn.Module):
             xz = torch.empty((2, Bp * L, D), dtype=x.dtype, device=x.device)
             a = x.view(Bp * L, dm)
             if D % 32 == 0:
-                gemm.run([gemm.Problem(a, self._w_in_nk, xz, planes=2)], name="gemm_inproj")
+                gemm.run([gemm.Problem(a, self._w_in_nk, xz, planes=2), *extra], name="gemm_inproj")
             else:          # a column tile may not straddle the two planes: two problems of one launch
-                gemm.run([gemm.Problem(a, w1, xz[0]), gemm.Problem(a, w2, xz[1])], name="gemm_inproj")
+                gemm.run([gemm.Problem(a, w1, xz[0]), gemm.Problem(a, w2, xz[1]), *extra], name="gemm_inproj")
         else:
+            assert not extra, "extra problems ride on the tensor-core launch only"
             x2 = x.reshape(1, Bp * L, dm).expand(2, Bp * L, dm)
             xz = torch.bmm(x2, self._w_in)                                           # (2, B'L, D)
         return xz[0].view(Bp, L, -1), xz[1].view(Bp, L, -1)
@@ -619,11 +630,12 @@ class SS2D_cond_v10(nn.Module):
             raise NotImplementedError(f"actalker_b200.{type(self).__name__} is forward-only (the reference's "
                                       "inference path, pipeline ...two_ip.py:351); call it under torch.no_grad()")
 
-    def forward(self, x, id_emb, conds, masks):
+    def forward(self, x, id_emb, conds, masks, out=None):
         # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
         # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
+        # out (extension, optional): contiguous (B', L, d_model) destination, e.g. this rank's slot of a gather buffer
         self._check_forward_only(x)
-        return self.scan_core(*self.project_inputs(x, id_emb, conds, masks), out_proj=True)
+        return self.scan_core(*self.project_inputs(x, id_emb, conds, masks), out_proj=True, out_buf=out)
 
 
 class SS2D_cond_v10_wo_id(SS2D_cond_v10):

@@ -29,20 +29,21 @@ from . import _lib
 from .mamba_layer import SS2D_cond_v10, _timed
 from .selective_scan_interface import _DTYPES, _ptr, _stream
 
-__all__ = ["ShardPlan", "ShardedSS2DCondV10", "all_gather_slices"]
+__all__ = ["ShardPlan", "ShardedSS2DCondV10", "BatchShardedCall", "all_gather_slices"]
 
 
 @dataclass(frozen=True)
 class ShardPlan:
-    """Partition of B' (batch mode) or of d_inner (channel mode) over `world` ranks."""
+    """Partition of B' (batch mode: balanced, remainder over the first ranks; block mode: equal blocks of ceil(B'/P) whose
+    slots tile an all-gather buffer) or of d_inner (channel mode) over `world` ranks."""
     mode: str
     world: int
     extent: int          # B' or d_inner
     granule: int = 1     # channel mode: slices are multiples of 8 channels (16-byte rows), equal on every rank
 
     def __post_init__(self):
-        if self.mode not in ("batch", "channel"):
-            raise ValueError("mode must be 'batch' or 'channel'")
+        if self.mode not in ("batch", "block", "channel"):
+            raise ValueError("mode must be 'batch', 'block' or 'channel'")
         if self.world < 1 or self.extent < 1:
             raise ValueError("world and extent must be positive")
         if self.mode == "channel" and self.extent % (self.world * self.granule) != 0:
@@ -56,6 +57,9 @@ class ShardPlan:
         if self.mode == "channel":
             w = self.extent // self.world
             return rank * w, (rank + 1) * w
+        if self.mode == "block":      # equal blocks of ceil(extent / world); the last ones shorter or empty
+            c = -(-self.extent // self.world)
+            return min(rank * c, self.extent), min((rank + 1) * c, self.extent)
         base, rem = divmod(self.extent, self.world)
         lo = rank * base + min(rank, rem)
         return lo, lo + base + (1 if rank < rem else 0)
@@ -71,6 +75,99 @@ def all_gather_slices(local: torch.Tensor, group=None) -> torch.Tensor:
     out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
     return out
+
+
+class BatchShardedCall:
+    """ONE layer call split batch-first over the ranks ("assign (batch x CFG) blocks first"): every rank
+    holds the call's full inputs (the denoiser around the layer is replicated), computes the layer for its block of whole
+    frames and the result is all-gathered, so that every rank leaves with the full (B', L, d_model) output — the strong
+    scaling of the live caller's B' = 4 x 25 = 100 call (pipeline ...two_ip.py:712).
+
+    Partition: equal blocks of ceil(B'/P) frames, the last blocks shorter or empty.  The gather buffer has P * ceil(B'/P)
+    frame slots and the result is its first B' frames, so the NCCL all-gather (equal contributions) writes the output in
+    place: no padding copy, no re-layout.  Frames are independent, so the result is bit-identical to the one-GPU call.
+    tiles > 1: a rank's block is cut into that many pieces; the gather of piece i runs on a side stream under the compute
+    of piece i+1 (the pieces' slots are strided in the output, so each piece gathers into its own buffer and one copy per
+    piece, also on the side stream, places it)."""
+
+    def __init__(self, layer: SS2D_cond_v10, group=None, tiles: int = 1):
+        self.layer, self.group, self.tiles = layer, group, max(1, int(tiles))
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._side = None
+        self._events = []
+
+    def plan(self, Bp: int) -> "ShardPlan":
+        return ShardPlan("block", self.world, Bp)
+
+    def phase_ms(self):
+        """Device time of the last call's phases on this rank: compute (all pieces) and the exposed tail after the last
+        piece's compute (its gather).  Needs a synchronised device."""
+        if not self._events:
+            return None
+        s, c, e = self._events
+        return {"compute": s.elapsed_time(c), "gather_tail": c.elapsed_time(e)}
+
+    def __call__(self, x, id_emb, conds, masks):
+        layer, P, rank = self.layer, self.world, self.rank
+        Bp, L, dm = x.shape
+        if P == 1:
+            return layer(x, id_emb, conds, masks)
+        cuda = x.is_cuda                                            # the gloo tests drive the same code on CPU tensors
+        chunk = -(-Bp // P)
+        lo, hi = self.plan(Bp).bounds(rank)
+        out = torch.empty((P * chunk, L, dm), dtype=x.dtype, device=x.device)
+        main = torch.cuda.current_stream(x.device) if cuda else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if cuda else None
+
+        def compute(a, b, dst):
+            """the layer for frames [a, b), written straight into dst (out_proj stores there: no copy)"""
+            if b > a:
+                y = layer(x[a:b], id_emb[a:b], conds[a:b], masks, out=dst[:b - a]) if cuda else layer(x[a:b], id_emb[a:b], conds[a:b], masks)
+                if y.data_ptr() != dst.data_ptr():
+                    dst[:b - a] = y
+
+        if cuda:
+            ev[0].record(main)
+        if self.tiles == 1:
+            mine = out[rank * chunk:(rank + 1) * chunk]
+            compute(lo, hi, mine)
+            if cuda:
+                ev[1].record(main)
+            with _timed("all_gather", x.device):       # in place: the rank's block already sits in its slot of the buffer
+                dist.all_gather_into_tensor(out.view(-1), mine.reshape(-1), group=self.group)
+        else:
+            if cuda and self._side is None:
+                self._side = torch.cuda.Stream(x.device)
+            side = self._side
+            tr = -(-chunk // self.tiles)                              # frames per piece (the last may be shorter / empty)
+            keep = []
+            for t in range(self.tiles):
+                a, b = min(lo + t * tr, hi), min(lo + (t + 1) * tr, hi)
+                mine = torch.empty((tr, L, dm), dtype=x.dtype, device=x.device)
+                compute(a, b, mine)
+                gathered = torch.empty((P, tr, L, dm), dtype=x.dtype, device=x.device)
+                n = min(tr, chunk - t * tr)
+                if cuda:
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    side.wait_event(done)
+                    with torch.cuda.stream(side):
+                        dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1), group=self.group)
+                        if n > 0:
+                            out.view(P, chunk, L, dm)[:, t * tr:t * tr + n] = gathered[:, :n]
+                else:
+                    dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1), group=self.group)
+                    if n > 0:
+                        out.view(P, chunk, L, dm)[:, t * tr:t * tr + n] = gathered[:, :n]
+                keep.append((mine, gathered))
+            if cuda:
+                ev[1].record(main)
+                main.wait_stream(side)
+        if cuda:
+            ev[2].record(main)
+            self._events = ev
+        return out[:Bp]
 
 
 class PeerGatherBuffers:

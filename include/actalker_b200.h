@@ -219,7 +219,8 @@ int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int D
  *   c : (M, N) row pitch ldc        or, with planes > 1, `planes` tensors of (M, N / planes) that are plane_stride
  *                                   elements apart (in_proj1 | in_proj2 from one stacked weight: x is read once)
  *   pitches in ELEMENTS and multiples of 8 (16 bytes); pointers 16-byte aligned; any M, N, K > 0.
- *   epilogue ACTK_GEMM_EPI_SILU: c = round(silu(round(a @ w^T))), the act(Linear(.)) of the condition tokens.
+ *   epilogue (per problem) ACTK_GEMM_EPI_SILU: c = round(silu(round(a @ w^T))), the act(Linear(.)) of the condition
+ *   tokens; problems of one launch run concurrently in no particular order (they must not depend on each other).
  *   dtype: ACTK_F16 / ACTK_BF16 (fp32 activations keep the caller's fp32 GEMM; ACTK_ERR_BAD_DTYPE).
  * ------------------------------------------------------------------------------------------- */
 #define ACTK_GEMM_MAX_PROBLEMS 4
@@ -230,10 +231,11 @@ typedef struct {
   void *c;
   long long lda, ldw, ldc, plane_stride;
   int M, N, K, planes;
+  int epilogue; /* ACTK_GEMM_EPI_* */
 } actk_gemm_problem;
 
 int actk_gemm_tn_supported(const actk_gemm_problem *problem, int dtype); /* 1 if the shape / alignment rules hold */
-int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, int epilogue, void *stream);
+int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) A-structure probe.  Writes *flag_dev = ACTK_A_POWER if |A[d][n] - (n+1)*A[d][0]| <=

@@ -167,3 +167,66 @@ def test_derived_weight_layout_for_the_fused_dt_proj():
         assert torch.equal(w[4 * N + k * Rp:4 * N + k * Rp + R], u.x_proj_weight[k, :R])
         assert not w[4 * N + k * Rp + R:4 * N + (k + 1) * Rp].any()
         assert torch.equal(dv["w_dt"][k * Rp:k * Rp + R, k * D:(k + 1) * D], u.dt_projs_weight[k].t())
+
+
+def test_gemm_argument_validation_and_struct_layout():
+    """actk_gemm_tn_fwd (header (3c)) rejects bad launches before touching a device; the ctypes struct mirrors the header."""
+    lib = _lib.load()
+    text = header_text()
+    body = re.search(r"typedef struct \{([^}]*)\} actk_gemm_problem;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = [n.strip(" *") for decl in body.split(";") if decl.strip() for n in decl.split(",")]
+    declared = [n.split()[-1].strip("*") for n in declared]
+    assert declared == [f[0] for f in _lib.GemmProblem._fields_], declared
+    assert int(re.search(r"ACTK_GEMM_MAX_PROBLEMS (\d+)", text).group(1)) == _lib.GEMM_MAX_PROBLEMS
+    arr = (_lib.GemmProblem * 1)()
+    assert lib.actk_gemm_tn_fwd(None, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
+    assert lib.actk_gemm_tn_fwd(arr, 0, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_F32, None) == _status("ACTK_ERR_BAD_DTYPE")
+    p = arr[0]
+    p.a, p.w, p.c = 1 << 20, 1 << 21, 1 << 22
+    p.M, p.N, p.K, p.planes, p.lda, p.ldw, p.ldc = 128, 64, 36, 1, 36, 36, 64
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ALIGN")   # 72-byte rows
+    assert not lib.actk_gemm_tn_supported(arr, _lib.ACTK_BF16)
+    p.K = p.lda = p.ldw = 40
+    assert lib.actk_gemm_tn_supported(arr, _lib.ACTK_BF16) and not lib.actk_gemm_tn_supported(arr, _lib.ACTK_F32)
+    p.planes, p.N = 2, 72                       # 36 columns per plane: a tile would straddle the planes
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_SHAPE")
+    p.planes, p.N, p.epilogue = 1, 64, 7
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
+
+
+def test_size_helpers_return_64_bit_values():
+    """Workspace / image sizes are `long long` in the header; a c_int restype would truncate anything >= 2 GiB."""
+    lib = _lib.load()
+    assert lib.actk_masked_scan_workspace_bytes.restype is C.c_longlong
+    assert lib.actk_dt_proj_image_bytes.restype is C.c_longlong
+    m = _lib.MaskedScanArgs()
+    m.Bp, m.D, m.nseg = 512, 2560, 400          # 512*4*400*2560*33*4 bytes = 276 GB: far above 2^31
+    assert lib.actk_masked_scan_workspace_bytes(C.byref(m)) == 512 * 4 * 400 * 2560 * 33 * 4
+
+
+def test_mask_index_lands_on_the_layers_device_and_weights_are_cached():
+    """A mask may live on another device than the activations (the reference's indexing moves the index tensor); the
+    cache key carries the target device.  Derived per-dtype weights are built once per parameter version."""
+    import torch
+    from actalker_b200 import SS2D_Unit
+    from actalker_b200.mask import MaskIndexCache
+    cache = MaskIndexCache()
+    m = torch.zeros(1, 1, 64, 64)
+    m[:, :, 16:48, 8:56] = 1
+    e = cache.get(m, 64, device="cpu")
+    assert e.idx.device.type == "cpu" and e.n_sel == 24 and e.selected.sum().item() == 24 and cache.misses == 1
+    assert cache.get(m, 64, device=torch.device("cpu")) is e and cache.misses == 1
+    with pytest.raises(RuntimeError, match="must be"):
+        cache.get(torch.ones(64, 64), 64)
+    u = SS2D_Unit(d_model=64, d_cond=64, cond_size=32, d_state=16, size=8, scan_type="sweep", num_direction=2)
+    w = u.weights_for(torch.bfloat16)
+    assert w is u.weights_for(torch.bfloat16) and w["w_xproj"].dtype == torch.bfloat16
+    assert w["w_dt_nk"].shape == (2 * 128, 2 * u.derived()["rank_pad"]) and torch.equal(w["w_dt_nk"], w["w_dt"].t())
+    half = u.weights_for(torch.bfloat16, 64, 128)           # channels [64, 128) of both directions
+    assert half["A"].shape == (128, 16) and torch.equal(half["A"][:64], u.derived()["A"][64:128])
+    assert torch.equal(half["w_dt_nk"][64:], w["w_dt_nk"][128 + 64:256])
+    with torch.no_grad():
+        u.Ds.add_(1.0)                                       # a parameter changed in place: everything is rebuilt
+    assert u.weights_for(torch.bfloat16) is not w

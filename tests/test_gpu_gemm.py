@@ -22,11 +22,11 @@ def _ref(a, w, dtype, silu=False):
     return y
 
 
-def _check(got, want, dtype, what):
+def _check(got, want, dtype, what, ulps=1):
     assert got.dtype == dtype and got.shape == want.shape, what
     assert torch.isfinite(got.float()).all(), f"{what}: non-finite"
     err = (got.float() - want.float()).abs()
-    tol = 2 * STEP[dtype] * want.float().abs() + 1e-3 * STEP[dtype] / 2.0 ** -11 + 1e-6
+    tol = ulps * 2 * STEP[dtype] * want.float().abs() + 1e-3 * STEP[dtype] / 2.0 ** -11 + 1e-6
     bad = (err > tol)
     assert not bad.any(), f"{what}: {int(bad.sum())} elements off, max err {err.max().item():.3e}"
     assert (got == want).float().mean() > 0.95, f"{what}: only {(got == want).float().mean().item():.3f} bit-identical"
@@ -67,7 +67,8 @@ def test_gemm_silu_epilogue_planes_and_strided_operands(dtype):
     w = (torch.randn(320, 128, generator=g) / 11.0).to(dtype).cuda()
     out = torch.full((700, 320), float("nan"), dtype=dtype, device="cuda")
     gemm.run([gemm.Problem(a, w, out)], silu=True)
-    _check(out.cpu(), _ref(a.cpu(), w.cpu(), dtype, silu=True), dtype, "silu")
+    # two roundings: a product that lands one ulp apart moves the SiLU of it by up to two (slope ~1.1 above x = 2)
+    _check(out.cpu(), _ref(a.cpu(), w.cpu(), dtype, silu=True), dtype, "silu", ulps=3)
     # (2) two output planes from one stacked weight (in_proj1 | in_proj2)
     w2 = (torch.randn(2 * 192, 128, generator=g) / 11.0).to(dtype).cuda()
     planes = torch.full((2, 700, 192), float("nan"), dtype=dtype, device="cuda")
@@ -112,9 +113,9 @@ def test_gemm_rejects_bad_arguments_loudly():
     with pytest.raises(RuntimeError, match="16 bytes"):
         gemm.run([gemm.Problem(a, w, out)])
     arr = (_lib.GemmProblem * 1)()
-    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_F32, 0, None) != 0            # fp32 is not this kernel's route
-    assert lib.actk_gemm_tn_fwd(arr, 5, _lib.ACTK_BF16, 0, None) != 0           # more problems than a launch holds
-    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, 0, None) != 0           # NULL pointers
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_F32, None) != 0            # fp32 is not this kernel's route
+    assert lib.actk_gemm_tn_fwd(arr, 5, _lib.ACTK_BF16, None) != 0           # more problems than a launch holds
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) != 0           # NULL pointers
     assert b"NULL" in lib.actk_last_error()
 
 

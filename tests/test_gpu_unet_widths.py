@@ -123,3 +123,15 @@ def test_config1_full_width_frames_match_oracle(dtype):
     with torch.no_grad():
         got = ours(x.cuda(), id_emb.cuda(), conds.cuda(), [m.cuda() for m in masks])
     close(got, want, dtype, tol=LAYER_TOL, what="configs[1] frames")
+
+
+def test_masks_on_the_cpu_work_like_upstream():
+    """The reference indexes `xz[:, idx, :]` with whatever device the mask lives on (indexing moves the index tensor); here
+    a host mask must give the same layer output as the same mask on the GPU — never a host pointer in a kernel."""
+    kw, sd, x, id_emb, conds, masks, want = _case(640, 36, 2, torch.float32, "rects", 72589 + 640)
+    ours = _ours(kw, sd, torch.float32)
+    with torch.no_grad():
+        on_gpu = ours(x.cuda(), id_emb.cuda(), conds.cuda(), [m.cuda() for m in masks])
+        on_cpu = ours(x.cuda(), id_emb.cuda(), conds.cuda(), masks)
+    assert torch.equal(on_gpu, on_cpu)
+    close(on_cpu, want, torch.float32, tol=LAYER_TOL, what="cpu masks")

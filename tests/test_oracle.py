@@ -229,9 +229,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "masked selective-scan Gtokens/s" and d["unit"] == "Gtokens/s"
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["n_gpus"] == 2 and d["value"] > 0
-    assert "18x18 tokens, d_model 1280" in d["config"]["workload"] and "frames per step" in d["config"]["sample"]
+    assert "18x18 tokens, d_model 1280" in d["config"]["workload"]
+    # two frames fit the time budget: every step is the full workload, and the config block is the GPU arm's own
+    assert d["same_config"] is True and d["frames_per_step"] == 2 and "sample" not in d["config"]
+    assert set(d["config"]) == {"workload", "tokens_per_step_per_gpu", "l2", "a_kind", "parallelism"}
+    assert d["full_workload_estimate"]["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames per step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Gtokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(d["value"] - 2 * 324 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-9
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600,

@@ -23,6 +23,9 @@ def test_shard_plan_bounds():
     assert sizes == [4, 3, 3, 3, 3, 3, 3, 3] and b.bounds(0)[0] == 0 and b.bounds(7)[1] == 25
     assert all(b.bounds(r)[1] == b.bounds(r + 1)[0] for r in range(7))
     assert ShardPlan("batch", 4, 100).all_bounds() == [(25 * r, 25 * r + 25) for r in range(4)]
+    blk = ShardPlan("block", 8, 100)                # equal blocks of ceil(100/8) = 13 frames, the last one shorter
+    assert [hi - lo for lo, hi in blk.all_bounds()] == [13] * 7 + [9] and blk.bounds(7) == (91, 100)
+    assert [hi - lo for lo, hi in ShardPlan("block", 8, 25).all_bounds()] == [4, 4, 4, 4, 4, 4, 1, 0]
     with pytest.raises(ValueError):
         ShardPlan("rows", 2, 8)
 
@@ -58,6 +61,24 @@ def _gloo_worker(rank, world, port, ret):
         mine[slice(*bp.bounds(rank))] = 1
         dist.all_reduce(mine)
         assert torch.equal(mine, torch.ones(7))
+        # ONE call split batch-first (BatchShardedCall): block plan, in-place all-gather into the padded buffer, tiled
+        # variant; a stand-in layer that treats frames independently, as the real one does
+        from actalker_b200.sharded import BatchShardedCall
+
+        class Fake(torch.nn.Module):
+            def forward(self, x, id_emb, conds, masks):
+                return x * 2.0 + id_emb.mean(dim=(1, 2), keepdim=True) + conds.sum(dim=(1, 2), keepdim=True) * masks[0].mean()
+
+        fake = Fake()
+        for Bp in (7, 3, 1):                                   # 4+3 frames, 2+1, 1+0 (an idle rank)
+            x, idm, cd = torch.randn(Bp, 5, 8), torch.randn(Bp, 1, 4), torch.randn(Bp, 3, 4)
+            masks = [torch.ones(1, 1, 2, 2), torch.ones(1, 1, 2, 2)]
+            want = fake(x, idm, cd, masks)
+            for tiles in (1, 2, 3):
+                call = BatchShardedCall(fake, tiles=tiles)
+                assert call.plan(Bp).bounds(rank) == (min(rank * -(-Bp // world), Bp), min((rank + 1) * -(-Bp // world), Bp))
+                got = call(x, idm, cd, masks)
+                assert got.shape == want.shape and torch.equal(got, want), (Bp, tiles)
         ret[rank] = True
     finally:
         dist.destroy_process_group()

@@ -49,6 +49,19 @@ __global__ void __launch_bounds__(128) rate_kernel(float *out, const float *in, 
         }
       }
       if (OP == 11) { v[i] = fma2(v[i], a2, b2); if ((i & 1) == 0) f[i] = ex2(f[i]); n[i] = (n[i] ^ kx) + ky; }  // 2 FFMA2 : 1 MUFU : 4 ALU
+      if (OP == 12) { n[i] = (n[i] ^ kx) + ky; }                                               // LOP3 + IADD alone: the ALU rate
+      if (OP == 13) {  // ex2.approx.ftz.f16x2: two half-precision exponentials per MUFU instruction?
+        uint32_t x = (uint32_t)n[i];
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x));
+        n[i] = (int)x;
+      }
+      if (OP == 14) {  // ex2.approx.ftz.bf16x2
+        uint32_t x = (uint32_t)n[i];
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(x));
+        n[i] = (int)x;
+      }
+      if (OP == 15) { v[i] = fma2(v[i], a2, b2); n[i] = __funnelshift_l(n[i], kx, 7); }        // FFMA2 + SHF: two pipes, one issue port
+      if (OP == 16) { f[i] = fmaf(f[i], a, b); n[i] = __funnelshift_l(n[i], kx, 7); }          // FFMA + SHF
       if (OP == 5) {  // the apply() pattern: FMUL2 (bcast) + FFMA2 + FFMA2 per state pair, operands from registers
         uint64_t d = mul2(a2, v[(i + 1) & 15]);
         v[i] = fma2(b2, v[i], d);
@@ -100,5 +113,10 @@ int main() {
   run<9>("group{MUFU,2 LOP3,2 IADD}", 16, out, in);
   run<10>("group{3 FFMA2,1 LDS.128,~2 LOP3}", 5, out, in);
   run<11>("group{2 FFMA2,1 MUFU,2 LOP3,2 IADD}", 8, out, in);
+  run<12>("group{LOP3,IADD}", 16, out, in);
+  run<13>("MUFU.EX2 f16x2 (2 exps/instr)", 16, out, in);
+  run<14>("MUFU.EX2 bf16x2 (2 exps/instr)", 16, out, in);
+  run<15>("group{FFMA2,SHF}", 16, out, in);
+  run<16>("group{FFMA,SHF}", 16, out, in);
   return cudaDeviceSynchronize() != cudaSuccess;
 }
