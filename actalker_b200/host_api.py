@@ -30,15 +30,37 @@ class HostStreamedLayer:
         self.slots = [None] * depth       # per slot: device input/output staging + the events guarding them
         self.count = 0
 
+    @staticmethod
+    def _packed_base(x, idm, conds):
+        """The three inputs as views of ONE host buffer (a caller that stages a step's inputs together): returns that
+        buffer, else None.  One H2D copy then moves them all (one DMA descriptor chain instead of three)."""
+        base = x._base
+        if base is None or idm._base is not base or conds._base is not base or base.dim() != 1:
+            return None
+        if not (x.is_contiguous() and idm.is_contiguous() and conds.is_contiguous()) or not (x.dtype == idm.dtype == conds.dtype == base.dtype):
+            return None
+        return base
+
     def _slot(self, i, x, idm, conds, ydtype):
         s = self.slots[i]
-        shapes = (tuple(x.shape), tuple(idm.shape), tuple(conds.shape), x.dtype)
+        base = self._packed_base(x, idm, conds)
+        shapes = (tuple(x.shape), tuple(idm.shape), tuple(conds.shape), x.dtype,
+                  None if base is None else (base.numel(), x.storage_offset(), idm.storage_offset(), conds.storage_offset()))
         if s is None or s["shapes"] != shapes:
             dev = self.device
-            s = {"shapes": shapes,
-                 "x": torch.empty(x.shape, dtype=x.dtype, device=dev),
-                 "idm": torch.empty(idm.shape, dtype=idm.dtype, device=dev),
-                 "conds": torch.empty(conds.shape, dtype=conds.dtype, device=dev),
+            if base is not None:      # device mirror of the packed buffer; the layer reads views at the same offsets
+                packed = torch.empty(base.numel(), dtype=base.dtype, device=dev)
+                view = lambda t: packed[t.storage_offset() - base.storage_offset():][:t.numel()].view(t.shape)
+                dx, di, dc = view(x), view(idm), view(conds)
+            else:
+                packed = None
+                dx = torch.empty(x.shape, dtype=x.dtype, device=dev)
+                di = torch.empty(idm.shape, dtype=idm.dtype, device=dev)
+                dc = torch.empty(conds.shape, dtype=conds.dtype, device=dev)
+            s = {"shapes": shapes, "packed": packed,
+                 "x": dx,
+                 "idm": di,
+                 "conds": dc,
                  "y": None,
                  "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event()}
             s["downloaded"].record(self.d2h)
@@ -54,9 +76,12 @@ class HostStreamedLayer:
         # inputs of this slot may be overwritten once the compute that read them has finished
         self.h2d.wait_event(s["computed"])
         with torch.cuda.stream(self.h2d):
-            s["x"].copy_(x, non_blocking=True)
-            s["idm"].copy_(idm, non_blocking=True)
-            s["conds"].copy_(conds, non_blocking=True)
+            if s["packed"] is not None:
+                s["packed"].copy_(x._base, non_blocking=True)
+            else:
+                s["x"].copy_(x, non_blocking=True)
+                s["idm"].copy_(idm, non_blocking=True)
+                s["conds"].copy_(conds, non_blocking=True)
             s["uploaded"].record(self.h2d)
         self.compute.wait_event(s["uploaded"])
         self.compute.wait_event(s["downloaded"])          # previous result of this slot has left the device

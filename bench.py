@@ -347,11 +347,12 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
         out[f"Bp{Bp}"] = {"ms_1gpu": res["t1"], "ms_Ngpu": res["tN"], "efficiency": res["t1"] / (world * res["tN"]),
                           "frames_per_rank": [hi - lo for lo, hi in call.plan(Bp).all_bounds()],
                           "gather_bytes_per_rank": Bp * L * d_model * x.element_size(),
-                          "bit_identical_to_one_gpu": bool(flag.item()), "phases_ms": call.phase_ms()}
+                          "bit_identical_to_one_gpu": bool(flag.item()), "phases_ms": call.phase_ms(),
+                          "tiles_per_rank": call.tiles}
         del x, idm, cd, res
     out["what"] = ("one call split batch-first (whole frames per rank), result all-gathered to every rank (NCCL over "
-                   f"NVLink) inside the timed region, {args.strong_tiles} tile(s) per rank so the gather of tile i runs "
-                   "under the compute of tile i+1; efficiency = t1 / (N * tN)")
+                   f"NVLink) inside the timed region; up to {args.strong_tiles} tiles per rank (>= 25 frames each) so the "
+                   "gather of tile i runs under the compute of tile i+1; efficiency = t1 / (N * tN)")
     return out
 
 

@@ -183,8 +183,34 @@ def test_bench_line_carries_the_contract_keys():
     assert abs(rf["achieved"] - rf["algorithmic_bytes"] / (rf["kernel_ms"] * 1e-3) / 1e9) < 1e-3 * rf["achieved"]
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
-    assert d["gpu_launches"] == 2 * d["steps"]
+    # this repo's launches per step on the 16-bit route: cond projections, in_proj (+ id_proj), x_proj, dt_proj, the
+    # masked scan, merge + LayerNorm, out_proj — all of them C-ABI launches of the in-tree library
+    assert d["gpu_launches"] == 7 * d["steps"] and d["gpu_launches_per_step"] == 7
+    per = rf["ms_per_step_by_kernel"]
+    assert set(per) == {"gemm_cond", "gemm_inproj", "gemm_xproj", "gemm_dtproj", "masked_scan", "merge_ln", "gemm_outproj"}
+    assert sum(per.values()) <= d["ms_per_step"] * 1.02           # the kernels of a step fit inside the step
     assert abs(d["value"] - 25 * 5184 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6
+    fl = rf["instruction_floor"]
+    assert 0.5 < fl["frac_of_floor"] <= 1.05 and fl["ms"] < rf["kernel_ms"] * 1.05
+    assert sorted(e["passes_ms"])[1] == round(e["ms_per_step"], 4) and e["reported_pass"] == "median"
+    assert 0 < e["host_link_frac"] <= 1.05 and e["host_link"]["ms_per_step"] > 0
+
+
+def test_bench_parity_field_compares_the_gpu_layer_with_the_cpu_oracle_on_the_bench_frames():
+    """With the CPU baseline enabled the bench line carries `parity`: the GPU layer against the oracle on the very frames
+    the cpu_baseline computed (full 72x72 frames of the bench workload), within the layer tolerance."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--no-config0",
+                        "--frames", "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    par, cb = d["parity"], d["cpu_baseline"]
+    assert par["ok"] is True and par["finite"] is True and par["frames"] >= 1
+    assert par["max_abs_err"] <= par["tol"]["atol"] + par["tol"]["rtol"] * par["max_abs_ref"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
 
 
 def test_reference_op_graph_on_the_upstream_derived_kernel_full_size(capsys):

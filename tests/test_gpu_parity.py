@@ -270,6 +270,14 @@ def test_host_streamed_layer_matches_direct_calls():
     ones = torch.ones(1, 1, 96, 96, device="cuda")
     work = [(torch.randn(3, 144, 64).pin_memory(), torch.randn(3, 1, 128).pin_memory(),
              torch.randn(3, 33, 128).pin_memory(), torch.empty(3, 144, 64).pin_memory()) for _ in range(5)]
+    # inputs staged together in ONE pinned buffer travel as one copy (the bench's e2e path): same results
+    for _ in range(3):
+        buf = torch.empty(3 * 144 * 64 + 3 * 128 + 3 * 33 * 128).pin_memory()
+        px, pi, pc = buf[:27648].view(3, 144, 64), buf[27648:28032].view(3, 1, 128), buf[28032:].view(3, 33, 128)
+        for t in (px, pi, pc):
+            t.copy_(torch.randn(t.shape))
+        assert HostStreamedLayer._packed_base(px, pi, pc) is buf
+        work.append((px, pi, pc, torch.empty(3, 144, 64).pin_memory()))
     runner = HostStreamedLayer(layer)
     for x, idm, cd, out in work:
         runner.submit(x, idm, cd, [ones, ones], out)
