@@ -26,6 +26,7 @@
 // Up to 4 independent problems per launch (both branches, latent + tail tokens) share one grid through a tile table.
 // Tails of M / N / K need no special code: TMA zero-fills loads and clips stores at the tensor bounds.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,9 +38,7 @@ constexpr int kBM = 128;               // rows per tile == MMA M
 constexpr int kBK = 64;                // K elements per slab: 128-byte rows, one SWIZZLE_128B atom wide
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kABytes = kBM * kBK * 2;
-constexpr int kEpiBufs = 3;
 constexpr uint32_t kEpiBufBytes = kBM * 64 * 2;        // one staging tile: 128 rows x 64 columns of 16-bit elements
-constexpr uint32_t kEpiBytes = kEpiBufs * kEpiBufBytes;
 constexpr int kMaxGemmProblems = ACTK_GEMM_MAX_PROBLEMS;
 
 struct GemmProblemDev {
@@ -58,6 +57,9 @@ struct alignas(64) GemmParams {
   GemmProblemDev p[kMaxGemmProblems];
   int n_problems, total_tiles, stages, epilogue;
   uint32_t stage_bytes;
+  int epi_bufs;        // staging tiles of the epilogue (3, or 2 when the ring needs the room)
+  int acc_bufs;        // accumulator buffers in tensor memory: 2 (tile i+1's MMAs under tile i's epilogue) or 1
+  int acc_hstride;     // MH == 2: tensor-memory columns between the accumulators of a tile's two row halves
 };
 
 __device__ __forceinline__ uint64_t gemm_sw128_desc(uint32_t smem_addr) {   // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
@@ -133,13 +135,17 @@ __device__ __forceinline__ int gemm_problem_of(const GemmParams &P, int t) {
   return g;
 }
 
-template <typename T, int EPI>
+// MH: row halves per tile.  1 (default): 128-row tiles, two accumulator buffers.  2 (ACTK_GEMM_MH=2): 256-row tiles —
+// every W slab feeds two M = 128 MMAs, which cuts the TMA fill traffic per multiply-add by a third (see launch_gemm for
+// what that measured).
+template <typename T, int EPI, int MH>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t gemm_smem[];
   const uint32_t base = (smem_u32(gemm_smem) + 1023u) & ~1023u;     // SWIZZLE_128B atoms want 1024-byte alignment
   const int S = P.stages;
   const uint32_t epi_base = base + (uint32_t)S * P.stage_bytes;
-  const uint32_t bar_base = epi_base + kEpiBytes;
+  const uint32_t bar_base = epi_base + (uint32_t)P.epi_bufs * kEpiBufBytes;
+  constexpr uint32_t kATile = MH * kABytes;
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * S, tfull_bar = bar_base + 16 * S,
                  tempty_bar = tfull_bar + 16;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gemm_smem + (tempty_bar + 16 - smem_u32(gemm_smem)));
@@ -170,14 +176,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
         const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
         const int local = tile - pr.tile_begin;
         const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
-        const uint32_t tx = kABytes + (uint32_t)pr.bn * (kBK * 2);
+        const uint32_t tx = kATile + (uint32_t)pr.bn * (kBK * 2);
         for (int ks = 0; ks < pr.k_slabs; ++ks, ++it) {
           const uint32_t s = it % S, use = it / S;
           if (use > 0) gemm_bar_wait(empty_bar + 8 * s, (use - 1) & 1);
           const uint32_t sa = base + s * P.stage_bytes;
           gemm_bar_expect_tx(full_bar + 8 * s, tx);
-          gemm_tma_load_2d(sa, &pr.a, ks * kBK, m * kBM, full_bar + 8 * s);
-          gemm_tma_load_2d(sa + kABytes, &pr.w, ks * kBK, n * pr.bn, full_bar + 8 * s);
+          gemm_tma_load_2d(sa, &pr.a, ks * kBK, m * (MH * kBM), full_bar + 8 * s);       // box of MH * 128 rows
+          gemm_tma_load_2d(sa + kATile, &pr.w, ks * kBK, n * pr.bn, full_bar + 8 * s);
         }
       }
     }
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
         const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(pr.bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-        const uint32_t b = tc & 1, ub = tc >> 1;
+        const uint32_t b = P.acc_bufs == 2 ? (tc & 1) : 0, ub = P.acc_bufs == 2 ? (tc >> 1) : tc;
         if (ub > 0) gemm_bar_wait(tempty_bar + 8 * b, (ub - 1) & 1);   // the epilogue has read this buffer's previous tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem + b * 256;
@@ -197,10 +203,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
           const uint32_t s = it % S, use = it / S;
           gemm_bar_wait(full_bar + 8 * s, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = base + s * P.stage_bytes, sw = sa + kABytes;
+          const uint32_t sa = base + s * P.stage_bytes, sw = sa + kATile;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            gemm_umma(acc, gemm_sw128_desc(sa + k * 32), gemm_sw128_desc(sw + k * 32), idesc, (uint32_t)((ks | k) != 0));
+#pragma unroll
+            for (int hh = 0; hh < MH; ++hh)
+              gemm_umma(acc + hh * P.acc_hstride, gemm_sw128_desc(sa + hh * kABytes + k * 32), gemm_sw128_desc(sw + k * 32), idesc,
+                        (uint32_t)((ks | k) != 0));
           gemm_commit(empty_bar + 8 * s);    // the slab may be overwritten once these MMAs have read it
         }
         gemm_commit(tfull_bar + 8 * b);      // accumulators of this tile complete
@@ -220,14 +229,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
       const int plane = n / pr.tiles_per_plane;
       const int col0 = (n - plane * pr.tiles_per_plane) * pr.bn;     // first column of the tile within its plane
-      const uint32_t b = tc & 1, ub = tc >> 1;
+      const uint32_t b = P.acc_bufs == 2 ? (tc & 1) : 0, ub = P.acc_bufs == 2 ? (tc >> 1) : tc;
       gemm_bar_wait(tfull_bar + 8 * b, ub & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256;
       const int nchunks = (pr.bn + 63) >> 6;
-      for (int cc = 0; cc < nchunks; ++cc, ++chunk_count) {
+      for (int hc = 0; hc < MH * nchunks; ++hc, ++chunk_count) {
+        const int hh = MH == 2 ? (hc >= nchunks ? 1 : 0) : 0, cc = hc - hh * nchunks;   // row half, 64-column chunk
+        const int row0 = (m * MH + hh) * kBM;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256 + hh * P.acc_hstride;
         const int width = pr.bn - cc * 64 >= 64 ? 64 : 32;          // bn is a multiple of 32
-        const uint32_t buf = epi_base + (chunk_count % kEpiBufs) * kEpiBufBytes;
+        const uint32_t buf = epi_base + (chunk_count % (uint32_t)P.epi_bufs) * kEpiBufBytes;
         if (h * 32 < width) {
           uint32_t v32[32];
           gemm_tmem_ld16(trow + cc * 64 + h * 32, v32);
@@ -254,13 +265,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
           }
           fence_proxy_async();
         }
-        // the leader makes sure the staging tile of the NEXT chunk is free (its store, three chunks back, has read it)
+        // the leader makes sure the staging tile of the NEXT chunk is free (its store, epi_bufs chunks back, has read it)
         // before anyone passes the barrier, then sends this chunk: one barrier per chunk
-        if (leader) bulk_wait_read<kEpiBufs - 2>();
+        if (leader) {
+          if (P.epi_bufs >= 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
         __syncwarp();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader && col0 + cc * 64 < pr.plane_cols) {
-          gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, m * kBM, plane, buf);
+        if (leader && col0 + cc * 64 < pr.plane_cols && row0 < pr.M) {
+          gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
           bulk_commit();
         }
       }
@@ -322,8 +335,14 @@ static const char *gemm_check(const actk_gemm_problem &p, int es) {
   return nullptr;
 }
 
-template <typename T>
-static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream_t stream) {
+// MH from the environment for tuning (ACTK_GEMM_MH=1|2), else by problem size
+static int gemm_forced_mh() {
+  const char *e = getenv("ACTK_GEMM_MH");
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+}
+
+template <typename T, int MH>
+static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms, int smem_max, int dev, cudaStream_t stream) {
   GemmEncodeFn fn = gemm_encode_fn();
   if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
   const CUtensorMapDataType dt = dtype == ACTK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -334,6 +353,7 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream
   for (int g = 0; g < n; ++g)
     if (pr[g].epilogue == ACTK_GEMM_EPI_SILU) epilogue = ACTK_GEMM_EPI_SILU;
   P.epilogue = epilogue;
+  constexpr int kRows = MH * kBM;          // rows per tile
   int tiles = 0, bn_max = 32;
   for (int g = 0; g < n; ++g) {
     const actk_gemm_problem &p = pr[g];
@@ -347,13 +367,13 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream
     d.tiles_per_plane = (pc + d.bn - 1) / d.bn;
     d.n_tiles = p.planes * d.tiles_per_plane;
     d.tile_begin = tiles;
-    tiles += ((p.M + kBM - 1) / kBM) * d.n_tiles;
+    tiles += ((p.M + kRows - 1) / kRows) * d.n_tiles;
     bn_max = d.bn > bn_max ? d.bn : bn_max;
     const cuuint32_t estr[3] = {1, 1, 1};
-    {   // A (K, M): slabs of 64 x 128
+    {   // A (K, M): slabs of 64 columns x (MH * 128) rows
       cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
       cuuint64_t strides[1] = {(cuuint64_t)p.lda * sizeof(T)};
-      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kRows};
       CUresult r = fn(&d.a, dt, 2, const_cast<void *>(p.a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (A of problem %d) failed with CUresult %d", g, (int)r);
@@ -378,18 +398,21 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream
     }
   }
   P.total_tiles = tiles;
-  P.stage_bytes = kABytes + (uint32_t)bn_max * (kBK * 2);
-  const size_t fixed = 1024 + kEpiBytes + 16 * 6 + 64;
-  int dev = 0, sms = 0, smem_max = 0;
-  ACTK_CUDA_OK(cudaGetDevice(&dev));
-  ACTK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  ACTK_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int stages = (int)(((size_t)smem_max - fixed) / P.stage_bytes);
+  P.stage_bytes = MH * kABytes + (uint32_t)bn_max * (kBK * 2);
+  // tensor memory: 512 columns.  Two accumulator buffers when a tile's accumulators fit in 256 columns, else one.
+  if (MH == 1) { P.acc_bufs = 2; P.acc_hstride = 0; }
+  else if (bn_max <= 128) { P.acc_bufs = 2; P.acc_hstride = 128; }
+  else { P.acc_bufs = 1; P.acc_hstride = 256; }
+  // shared memory: ring stages + epilogue staging tiles; three staging tiles unless that leaves fewer than three stages
+  const size_t bars = 16 * 6 + 64;
+  auto stages_for = [&](int bufs) { return (int)(((size_t)smem_max - 1024 - (size_t)bufs * kEpiBufBytes - bars) / P.stage_bytes); };
+  P.epi_bufs = stages_for(3) >= 3 ? 3 : 2;
+  int stages = stages_for(P.epi_bufs);
   stages = stages > 6 ? 6 : stages;
   if (stages < 2) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: %d bytes of shared memory per block do not hold two pipeline stages", smem_max);
   P.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * P.stage_bytes + kEpiBytes + 16 * (size_t)stages + 64;
-  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE>;
+  const size_t smem = 1024 + (size_t)stages * P.stage_bytes + (size_t)P.epi_bufs * kEpiBufBytes + 16 * (size_t)stages + 64;
+  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH>;
   static int configured[64][2] = {};   // per device and epilogue: dynamic shared memory limit raised
   const int ei = epilogue == ACTK_GEMM_EPI_SILU ? 1 : 0;
   if (dev < 64 && !configured[dev][ei]) {
@@ -399,6 +422,22 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream
   kern<<<tiles < sms ? tiles : sms, kGemmThreads, smem, stream>>>(P);
   ACTK_CUDA_OK(cudaGetLastError());
   return ACTK_OK;
+}
+
+template <typename T>
+static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream_t stream) {
+  int dev = 0, sms = 0, smem_max = 0;
+  ACTK_CUDA_OK(cudaGetDevice(&dev));
+  ACTK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ACTK_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // 128-row tiles by default.  256-row tiles (ACTK_GEMM_MH=2) were built to halve the W fill traffic and measured on B200
+  // (profiles/r02_gemm_tn_mh.txt): out_proj 71.9 -> 68.4 us, x_proj 76.6 -> 74.8, but in_proj 142.7 -> 148.8 and dt_proj
+  // 128 -> 171 us (one accumulator buffer: the epilogue no longer hides under the next tile's MMAs).  What bounds the
+  // K >= 320 products is the MMAs' own operand reads from shared memory (12 KB per M128 N256 K16 instruction), which a taller
+  // tile does not change.
+  int mh = 1;
+  return mh == 2 ? launch_gemm_mh<T, 2>(pr, n, dtype, sms, smem_max, dev, stream)
+                 : launch_gemm_mh<T, 1>(pr, n, dtype, sms, smem_max, dev, stream);
 }
 
 }  // namespace actk

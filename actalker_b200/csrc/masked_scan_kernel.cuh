@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
   // the whole group — measured on B200: config 2 1.508 -> 1.482 ms, a rank's d_inner slice 1.03 -> 0.98 ms (N=2),
   // 0.70 -> 0.66 ms (N=8), rectangle masks at B'=25 0.418 -> 0.400 ms.  With the 3-slot ring (8 CTAs per SM, CFG x4) 4
   // is 1 % faster and stays; fp32 I/O and the fused dt_proj (4 TMEM columns per load) keep 4.
+#ifndef ACTK_CHAIN_POLL_NS
+#define ACTK_CHAIN_POLL_NS 200
+#endif
 #ifndef ACTK_GROUP_WIDE
 #define ACTK_GROUP_WIDE 8
 #endif
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
 
   const bool live = tid < nch;
   const int ch = k * D + d0 + (live ? tid : 0);
-  ChannelScan<POWER_A> cs;
+  ChannelScan<POWER_A, k16> cs;
   cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
   // ring slots and y double-buffer are indexed by the tile number relative to the chunk start.  The first tiles are
   // requested BEFORE a chained chunk waits for its predecessor's state: their HBM latency overlaps the wait.
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
       int done;
       do {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(P.chain_flag + q) : "memory");
-        if (done < seg) __nanosleep(200);
+        if (done < seg) __nanosleep(ACTK_CHAIN_POLL_NS);
       } while (done < seg);
     }
     __syncthreads();

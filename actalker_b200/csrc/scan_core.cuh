@@ -36,7 +36,12 @@ struct StepIn {
   float dt, x, u;
 };
 
-template <bool POWER_A>
+#ifndef ACTK_FAST_SOFTPLUS16
+#define ACTK_FAST_SOFTPLUS16 1   // 16-bit I/O: softplus without the small-argument series (see softplus20_io16)
+#endif
+
+// IO16: the activations are 16-bit tensors (selects the softplus form; all arithmetic stays fp32)
+template <bool POWER_A, bool IO16 = false>
 struct ChannelScan {
   uint64_t h[kN / 2];
   uint64_t a2[POWER_A ? 1 : kN / 2];  // general: A[d][n]*log2e, packed pairs
@@ -59,7 +64,7 @@ struct ChannelScan {
   __device__ __forceinline__ StepIn prologue(float u, float delta_raw) const {
     StepIn s;
     float dt = delta_raw + bias;
-    if (SOFTPLUS) dt = softplus20(dt);
+    if (SOFTPLUS) dt = (IO16 && ACTK_FAST_SOFTPLUS16) ? softplus20_io16(dt) : softplus20(dt);
     s.dt = dt;
     s.u = u;
     s.x = dt * u;

@@ -45,9 +45,20 @@ SHAPES = [
 ]
 
 
+@pytest.fixture(params=["auto", "1", "2"])
+def tile_rows(request, monkeypatch):
+    """Both tile heights of the kernel (128-row tiles with two accumulator buffers, 256-row tiles that share every W slab
+    between two MMAs) on every shape, whatever the size heuristic would pick."""
+    if request.param != "auto":
+        monkeypatch.setenv("ACTK_GEMM_MH", request.param)
+    else:
+        monkeypatch.delenv("ACTK_GEMM_MH", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_gemm_matches_fp32_reference(shape, dtype):
+def test_gemm_matches_fp32_reference(shape, dtype, tile_rows):
     from actalker_b200 import gemm
     M, N, K = shape
     g = torch.Generator().manual_seed(M + N + K)
@@ -59,7 +70,7 @@ def test_gemm_matches_fp32_reference(shape, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_gemm_silu_epilogue_planes_and_strided_operands(dtype):
+def test_gemm_silu_epilogue_planes_and_strided_operands(dtype, tile_rows):
     from actalker_b200 import gemm
     g = torch.Generator().manual_seed(3)
     # (1) SiLU epilogue: round(silu(round(a @ w^T)))
@@ -86,7 +97,7 @@ def test_gemm_silu_epilogue_planes_and_strided_operands(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
-def test_gemm_grouped_launch_and_many_tiles_per_cta(dtype):
+def test_gemm_grouped_launch_and_many_tiles_per_cta(dtype, tile_rows):
     """Four problems of different sizes in ONE launch (the x_proj / dt_proj launches of the layer), with more tiles than
     SMs so that every CTA walks the ring and both accumulator buffers many times."""
     from actalker_b200 import gemm
