@@ -59,7 +59,7 @@ class MergeLnArgs(C.Structure):
 
 class GemmProblem(C.Structure):
     _fields_ = [("a", _vp), ("w", _vp), ("c", _vp), ("lda", _ll), ("ldw", _ll), ("ldc", _ll), ("plane_stride", _ll),
-                ("M", _i), ("N", _i), ("K", _i), ("planes", _i), ("epilogue", _i)]
+                ("M", _i), ("N", _i), ("K", _i), ("planes", _i), ("epilogue", _i), ("peer_c", _vp * 8), ("n_peers", _i)]
 
 
 GEMM_MAX_PROBLEMS = 4

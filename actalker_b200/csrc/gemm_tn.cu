@@ -57,6 +57,10 @@ struct alignas(64) GemmParams {
   GemmProblemDev p[kMaxGemmProblems];
   int n_problems, total_tiles, stages, epilogue;
   uint32_t stage_bytes;
+  // Fused all-gather (multi-GPU, batch-first split of one call): problem 0's output tiles are stored to n_peers gather
+  // buffers — every rank's, own included, mapped into this process over NVLink peer memory — instead of one tensor.
+  CUtensorMap peer_c[ACTK_GEMM_MAX_PEERS];
+  int n_peers;
   int epi_bufs;        // staging tiles of the epilogue (3, or 2 when the ring needs the room)
   int acc_bufs;        // accumulator buffers in tensor memory: 2 (tile i+1's MMAs under tile i's epilogue) or 1
   int acc_hstride;     // MH == 2: tensor-memory columns between the accumulators of a tile's two row halves
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     for (int g = 0; g < P.n_problems; ++g) {
       tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); tmap_prefetch(&P.p[g].c32);
     }
+    for (int pe = 0; pe < P.n_peers; ++pe) tmap_prefetch(&P.peer_c[pe]);
   }
   __syncwarp();
   if (warp == 1) {   // 2 accumulator buffers x 256 columns
@@ -273,7 +278,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
         __syncwarp();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader && col0 + cc * 64 < pr.plane_cols && row0 < pr.M) {
-          gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
+          if (P.n_peers > 0) {      // the same staging tile goes to every rank's buffer: GEMM and all-gather in one kernel
+            for (int pe = 0; pe < P.n_peers; ++pe) gemm_tma_store_3d(&P.peer_c[pe], col0 + cc * 64, row0, plane, buf);
+          } else {
+            gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
+          }
           bulk_commit();
         }
       }
@@ -322,7 +331,13 @@ static int gemm_pick_bn(int N, int plane_cols) {
 }
 
 static const char *gemm_check(const actk_gemm_problem &p, int es) {
-  if (!p.a || !p.w || !p.c) return "NULL pointer";
+  if (p.n_peers < 0 || p.n_peers > ACTK_GEMM_MAX_PEERS) return "n_peers out of range";
+  if (!p.a || !p.w || (!p.c && p.n_peers == 0)) return "NULL pointer";
+  for (int i = 0; i < p.n_peers; ++i) {
+    if (!p.peer_c[i]) return "NULL pointer (peer buffer)";
+    if (reinterpret_cast<uintptr_t>(p.peer_c[i]) & 15) return "peer pointer not aligned to 16 bytes";
+  }
+  if (p.n_peers > 0 && (p.planes != 1 || p.N % 64 != 0)) return "the fused all-gather needs one plane and N a multiple of 64";
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "non-positive size";
   if (p.lda < p.K || p.ldw < p.K) return "row pitch smaller than K";
   if (p.planes < 1 || p.N % p.planes != 0) return "N is not a multiple of planes";
@@ -330,7 +345,7 @@ static const char *gemm_check(const actk_gemm_problem &p, int es) {
   if (p.ldc < pc) return "ldc smaller than the columns of a plane";
   if (p.planes > 1 && pc % 32 != 0) return "columns per plane must be a multiple of 32 when planes > 1";
   if ((p.lda * es) % 16 || (p.ldw * es) % 16 || (p.ldc * es) % 16 || (p.plane_stride * es) % 16) return "row pitch not a multiple of 16 bytes";
-  if ((reinterpret_cast<uintptr_t>(p.a) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.c)) & 15)
+  if ((reinterpret_cast<uintptr_t>(p.a) | reinterpret_cast<uintptr_t>(p.w) | (p.n_peers ? 0 : reinterpret_cast<uintptr_t>(p.c))) & 15)
     return "pointer not aligned to 16 bytes";
   return nullptr;
 }
@@ -386,7 +401,19 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (W of problem %d) failed with CUresult %d", g, (int)r);
     }
-    for (int narrow = 0; narrow < 2; ++narrow) {   // C (plane_cols, M, planes): 128-row store boxes of 64 / 32 columns
+    if (p.n_peers > 0) {   // one 64-column store map per rank's gather buffer (same shape and pitch as the local output)
+      if (g != 0 || n != 1) ACTK_FAIL(ACTK_ERR_BAD_ARG, "gemm_tn: the fused all-gather takes one problem per launch");
+      P.n_peers = p.n_peers;
+      for (int pe = 0; pe < p.n_peers; ++pe) {
+        cuuint64_t dims[3] = {(cuuint64_t)pc, (cuuint64_t)p.M, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)p.ldc * sizeof(T), (cuuint64_t)p.ldc * p.M * sizeof(T)};
+        cuuint32_t box[3] = {64u, (cuuint32_t)kBM, 1};
+        CUresult r = fn(&P.peer_c[pe], dt, 3, p.peer_c[pe], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (peer %d) failed with CUresult %d", pe, (int)r);
+      }
+    }
+    for (int narrow = 0; narrow < 2 && p.n_peers == 0; ++narrow) {   // C (plane_cols, M, planes): 128-row store boxes of 64 / 32 columns
       cuuint64_t dims[3] = {(cuuint64_t)pc, (cuuint64_t)p.M, (cuuint64_t)p.planes};
       cuuint64_t strides[2] = {(cuuint64_t)p.ldc * sizeof(T),
                                (cuuint64_t)(p.planes > 1 ? p.plane_stride : (long long)p.ldc * p.M) * sizeof(T)};

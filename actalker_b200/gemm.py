@@ -24,10 +24,13 @@ class Problem:
     """C = A @ W^T.  a: (M, K) view with unit column stride; w: (N, K) with unit column stride;
     out: (M, N) view with unit column stride, or (planes, M, N / planes) contiguous planes."""
 
-    __slots__ = ("a", "w", "out", "planes", "silu")
+    __slots__ = ("a", "w", "out", "planes", "silu", "peers", "ldc")
 
-    def __init__(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, planes: int = 1, silu: bool = False):
-        self.a, self.w, self.out, self.planes, self.silu = a, w, out, planes, silu
+    def __init__(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, planes: int = 1, silu: bool = False,
+                 peers: Sequence[int] = (), ldc: int = 0):
+        """peers: device addresses of the (M, N) output slot in every rank's gather buffer (fused GEMM + all-gather over
+        NVLink peer memory; `out` is then None and `ldc` the row pitch of those slots, N when 0)."""
+        self.a, self.w, self.out, self.planes, self.silu, self.peers, self.ldc = a, w, out, planes, silu, tuple(peers), ldc
 
     def fill(self, p: "_lib.GemmProblem"):
         a, w, out = self.a, self.w, self.out
@@ -35,7 +38,11 @@ class Problem:
         N = w.shape[0]
         if a.dim() != 2 or w.dim() != 2 or w.shape[1] != K or a.stride(1) != 1 or w.stride(1) != 1:
             raise RuntimeError(f"gemm: a {tuple(a.shape)}/{a.stride()} and w {tuple(w.shape)}/{w.stride()} must be 2-D with unit column stride")
-        if self.planes == 1:
+        if self.peers:
+            if out is not None or self.planes != 1:
+                raise RuntimeError("gemm: a problem with peer buffers has no local output tensor and one plane")
+            ldc, plane_stride = self.ldc or N, 0
+        elif self.planes == 1:
             if tuple(out.shape) != (M, N) or out.stride(1) != 1:
                 raise RuntimeError(f"gemm: out {tuple(out.shape)}/{out.stride()} must be ({M}, {N}) with unit column stride")
             ldc, plane_stride = out.stride(0), 0
@@ -44,7 +51,10 @@ class Problem:
                 raise RuntimeError(f"gemm: out {tuple(out.shape)} must be contiguous ({self.planes}, {M}, {N // self.planes})")
             ldc, plane_stride = out.stride(1), out.stride(0)
         # a one-row operand may carry any row stride; the kernel only needs a pitch that satisfies its checks
-        p.a, p.w, p.c = a.data_ptr(), w.data_ptr(), out.data_ptr()
+        p.a, p.w, p.c = a.data_ptr(), w.data_ptr(), (None if self.peers else out.data_ptr())
+        p.n_peers = len(self.peers)
+        for i, ptr in enumerate(self.peers):
+            p.peer_c[i] = ptr
         p.lda = a.stride(0) if M > 1 else K
         p.ldw = w.stride(0) if N > 1 else K
         p.ldc = ldc if M > 1 else N // self.planes

@@ -477,7 +477,7 @@ class SS2D_cond_v10(nn.Module):
         self.mask_cache = MaskIndexCache()
 
     def scan_core(self, xz1, xz2, tail1, tail2, m1: MaskIndex, m2: MaskIndex, ch_slice=None, weights=None,
-                  layernorm=None, out_proj=False, push=None, out_buf=None):
+                  layernorm=None, out_proj=False, push=None, out_buf=None, out_peers=None):
         """Both branches' gather -> bidirectional scan -> scatter, then direction/branch merge.
         ch_slice=None: + out_norm, returns (Bp, L, D) normalised.
         ch_slice=(lo, hi): returns the merged sums of channels [lo, hi) only, (Bp, L, hi-lo), NOT normalised —
@@ -520,13 +520,24 @@ class SS2D_cond_v10(nn.Module):
             return y
         with torch.cuda.device(xz1.device), _timed("merge_ln", xz1.device):
             _lib.check(lib.actk_merge_layernorm_fwd(ct.byref(a), _stream(xz1)), "actk_merge_layernorm_fwd")
-        return self._out_proj(out, out=out_buf) if out_proj else out
+        return self._out_proj(out, out=out_buf, peers=out_peers) if out_proj else out
 
-    def _out_proj(self, y, out=None):
+    def _out_proj(self, y, out=None, peers=None):
         """out_proj (mamba_layer.py:1985): tensor-core kernel for 16-bit activations, torch otherwise.
-        out: optional (B', L, d_model) contiguous destination (a slot of a multi-GPU gather buffer)."""
+        out: optional (B', L, d_model) contiguous destination (a slot of a multi-GPU gather buffer).
+        peers: device addresses of this call's (B'*L, d_model) slot in EVERY rank's gather buffer — the projection's
+        epilogue then stores each tile to all of them over NVLink peer memory (GEMM + all-gather in one kernel) and
+        nothing is returned."""
         w = self.out_proj.weight
-        if TC_GEMM and self.out_proj.bias is None and gemm.usable(y, w) and y.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
+        tc = TC_GEMM and self.out_proj.bias is None and gemm.usable(y, w) and y.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0
+        if peers is not None:
+            if not tc or w.shape[0] % 64 != 0:
+                raise NotImplementedError("the fused out_proj + all-gather needs the 16-bit tensor-core route and d_model % 64 == 0")
+            a = y.reshape(-1, y.shape[-1])
+            gemm.run([gemm.Problem(a if a.is_contiguous() else a.contiguous(), w if w.is_contiguous() else w.contiguous(),
+                                   None, peers=peers)], name="gemm_outproj")
+            return None
+        if tc:
             return gemm.linear(y, w, name="gemm_outproj", out=out)
         res = self.out_proj(y)
         if out is not None:
@@ -630,12 +641,13 @@ class SS2D_cond_v10(nn.Module):
             raise NotImplementedError(f"actalker_b200.{type(self).__name__} is forward-only (the reference's "
                                       "inference path, pipeline ...two_ip.py:351); call it under torch.no_grad()")
 
-    def forward(self, x, id_emb, conds, masks, out=None):
+    def forward(self, x, id_emb, conds, masks, out=None, out_peers=None):
         # x: (B', L, d_model); id_emb: (B', 1, d_cond); conds: (B', 33, d_cond) = 32 audio + 1 expression
         # tokens; masks: [audio (1,1,H,W), expression (1,1,H,W)]  (TransformerSTmodel.py:4121)
         # out (extension, optional): contiguous (B', L, d_model) destination, e.g. this rank's slot of a gather buffer
         self._check_forward_only(x)
-        return self.scan_core(*self.project_inputs(x, id_emb, conds, masks), out_proj=True, out_buf=out)
+        # out_peers (extension, optional): see _out_proj — the result goes to every rank's gather buffer instead
+        return self.scan_core(*self.project_inputs(x, id_emb, conds, masks), out_proj=True, out_buf=out, out_peers=out_peers)
 
 
 class SS2D_cond_v10_wo_id(SS2D_cond_v10):

@@ -93,9 +93,17 @@ class BatchShardedCall:
     MIN_FRAMES_PER_TILE = 25   # below ~1000 scan CTAs per launch the scan is latency-bound: cutting further costs more than
                                # the overlapped gather saves (B200, N=2, B'=25: 13 frames in two pieces 1.75 ms, in one 1.2 ms)
 
-    def __init__(self, layer: SS2D_cond_v10, group=None, tiles: int = 1):
-        self.layer, self.group, self.max_tiles = layer, group, max(1, int(tiles))
+    def __init__(self, layer: SS2D_cond_v10, group=None, tiles: int = 1, gather: str = "nccl"):
+        """gather="nccl": NCCL all-gather of the blocks (in place in the padded output).
+        gather="p2p": fused compute + collective — the out_proj kernel's epilogue stores every output tile straight into
+        all ranks' gather buffers over NVLink peer memory (one TMA store per rank and tile; CUDA IPC buffers of
+        PeerGatherBuffers), then a stream-ordered 4-byte all-reduce orders readers behind writers.  The returned tensor
+        aliases this rank's buffer and stays valid until the call after next (buffers alternate)."""
+        if gather not in ("nccl", "p2p"):
+            raise ValueError("gather must be 'nccl' or 'p2p'")
+        self.layer, self.group, self.max_tiles, self.gather = layer, group, max(1, int(tiles)), gather
         self.tiles = self.max_tiles
+        self._peer = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._side = None
@@ -134,6 +142,23 @@ class BatchShardedCall:
 
         if cuda:
             ev[0].record(main)
+        if self.gather == "p2p" and cuda:
+            self.tiles = 1
+            numel = P * chunk * L * dm
+            if self._peer is None or self._peer.numel != numel or self._peer.dtype != x.dtype:
+                if self._peer is not None:
+                    self._peer.close()
+                self._peer = PeerGatherBuffers(P, rank, numel, x.dtype, x.device, self.group)
+            ptrs, mine = self._peer.next()
+            off = rank * chunk * L * dm * x.element_size()          # this rank's block, same offset in every buffer
+            if hi > lo:
+                layer(x[lo:hi], id_emb[lo:hi], conds[lo:hi], masks, out_peers=[p + off for p in ptrs])
+            ev[1].record(main)
+            with _timed("all_gather", x.device):
+                self._peer.fence()
+            ev[2].record(main)
+            self._events = ev
+            return _device_view(mine, (P * chunk, L, dm), x.dtype, x.device)[:Bp]
         if self.tiles == 1:
             mine = out[rank * chunk:(rank + 1) * chunk]
             compute(lo, hi, mine)
@@ -173,6 +198,24 @@ class BatchShardedCall:
             ev[2].record(main)
             self._events = ev
         return out[:Bp]
+
+
+def _device_view(ptr: int, shape, dtype, device) -> torch.Tensor:
+    """A torch tensor over memory this library allocated (a peer gather buffer): the CUDA array interface with a 16-bit
+    integer type string, reinterpreted as the activation dtype (bf16 has no numpy type string)."""
+    numel = 1
+    for n in shape:
+        numel *= n
+    es = torch.empty(0, dtype=dtype).element_size()
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": {2: "<i2", 4: "<i4"}[es], "data": (int(ptr), False), "version": 2}
+    with torch.cuda.device(device):
+        t = torch.as_tensor(h, device=device)
+    return t.view(dtype).view(shape)
 
 
 class PeerGatherBuffers:

@@ -325,9 +325,13 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
         idm = torch.randn(Bp, 1, 1024, generator=g).to(dtype).to(dev)
         cd = torch.randn(Bp, 33, 1024, generator=g).to(dtype).to(dev)
         call = BatchShardedCall(layer, tiles=args.strong_tiles)
+        push = BatchShardedCall(layer, gather="p2p") if d_model % 64 == 0 and dtype != torch.float32 else None
         res = {}
         with torch.no_grad():
-            for name, fn in (("t1", lambda: layer(x, idm, cd, masks)), ("tN", lambda: call(x, idm, cd, masks))):
+            for name, fn in (("t1", lambda: layer(x, idm, cd, masks)), ("tN", lambda: call(x, idm, cd, masks)),
+                             ("tP", (lambda: push(x, idm, cd, masks)) if push else None)):
+                if fn is None:
+                    continue
                 for _ in range(3):
                     y = fn()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -345,6 +349,8 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
             # scan launch shape, within fp32 re-association when a rank's few frames take the two-level scan instead
             same = bool(torch.equal(res["t1_y"], res["tN_y"]))
             diff = (res["t1_y"].float() - res["tN_y"].float()).abs().max()
+            if push:
+                same = same and bool(torch.equal(res["tN_y"], res["tP_y"]))    # same kernels, other transport
         flag = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
@@ -354,6 +360,10 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
                           "bit_identical_to_one_gpu": bool(flag.item()), "max_abs_diff_vs_one_gpu": diff.item(),
                           "phases_ms": call.phase_ms(),
                           "tiles_per_rank": call.tiles}
+        if push:   # fused out_proj + all-gather over NVLink peer memory (TMA stores into every rank's buffer)
+            out[f"Bp{Bp}"]["fused_push"] = {"ms_Ngpu": res["tP"], "efficiency": res["t1"] / (world * res["tP"]),
+                                            "phases_ms": push.phase_ms()}
+            push._peer.close()
         del x, idm, cd, res
     out["what"] = ("one call split batch-first (whole frames per rank), result all-gathered to every rank (NCCL over "
                    f"NVLink) inside the timed region; up to {args.strong_tiles} tiles per rank (>= 25 frames each) so the "

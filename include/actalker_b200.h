@@ -224,6 +224,7 @@ int actk_gathered_layernorm_fwd(const void *in, int parts, long long rows, int D
  *   dtype: ACTK_F16 / ACTK_BF16 (fp32 activations keep the caller's fp32 GEMM; ACTK_ERR_BAD_DTYPE).
  * ------------------------------------------------------------------------------------------- */
 #define ACTK_GEMM_MAX_PROBLEMS 4
+#define ACTK_GEMM_MAX_PEERS 8
 #define ACTK_GEMM_EPI_NONE 0
 #define ACTK_GEMM_EPI_SILU 1
 typedef struct {
@@ -232,6 +233,12 @@ typedef struct {
   long long lda, ldw, ldc, plane_stride;
   int M, N, K, planes;
   int epilogue; /* ACTK_GEMM_EPI_* */
+  /* Fused GEMM + all-gather (multi-GPU; one problem per launch, planes == 1, N % 64 == 0): with n_peers > 0 every
+   * output tile is stored with one TMA store per rank into peer_c[p], p < n_peers — the (M, N) slot, row pitch ldc, of
+   * rank p's gather buffer mapped into this process (actk_peer_buffer_*; own rank included) — and `c` is not written.
+   * The caller orders the readers behind all writers (a stream-ordered barrier collective). */
+  void *peer_c[ACTK_GEMM_MAX_PEERS];
+  int n_peers;
 } actk_gemm_problem;
 
 int actk_gemm_tn_supported(const actk_gemm_problem *problem, int dtype); /* 1 if the shape / alignment rules hold */

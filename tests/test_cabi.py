@@ -176,8 +176,9 @@ def test_gemm_argument_validation_and_struct_layout():
     body = re.search(r"typedef struct \{([^}]*)\} actk_gemm_problem;", text, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     declared = [n.strip(" *") for decl in body.split(";") if decl.strip() for n in decl.split(",")]
-    declared = [n.split()[-1].strip("*") for n in declared]
+    declared = [re.sub(r"\[.*\]", "", n.split()[-1].strip("*")) for n in declared]
     assert declared == [f[0] for f in _lib.GemmProblem._fields_], declared
+    assert int(re.search(r"ACTK_GEMM_MAX_PEERS (\d+)", text).group(1)) == 8 == len(_lib.GemmProblem().peer_c)
     assert int(re.search(r"ACTK_GEMM_MAX_PROBLEMS (\d+)", text).group(1)) == _lib.GEMM_MAX_PROBLEMS
     arr = (_lib.GemmProblem * 1)()
     assert lib.actk_gemm_tn_fwd(None, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
@@ -194,6 +195,12 @@ def test_gemm_argument_validation_and_struct_layout():
     assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_SHAPE")
     p.planes, p.N, p.epilogue = 1, 64, 7
     assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
+    p.epilogue, p.n_peers = 0, 9                # fused all-gather: at most 8 ranks, non-NULL slots, N % 64 == 0
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_SHAPE")
+    p.n_peers = 2
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG") and b"peer" in lib.actk_last_error()
+    p.peer_c[0], p.peer_c[1], p.N = 1 << 23, 1 << 24, 96
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_SHAPE")
 
 
 def test_size_helpers_return_64_bit_values():
