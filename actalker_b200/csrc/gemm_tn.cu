@@ -317,12 +317,13 @@ static GemmEncodeFn gemm_encode_fn() {
   return fn;
 }
 
-// column-tile width: the fewest tiles of at most 256 columns, then the least padding; multiples of 32; when the output
-// is split into planes a tile must not straddle two of them
-static int gemm_pick_bn(int N, int plane_cols) {
+// column-tile width: the fewest tiles of at most 256 columns, then the least padding; multiples of 32 (of 64 for the fused
+// all-gather, whose per-rank store maps are 64 columns wide); when the output is split into planes a tile must not
+// straddle two of them
+static int gemm_pick_bn(int N, int plane_cols, int step = 32) {
   const int span = plane_cols;                         // tiles are laid out per plane
-  int best = 32, best_tiles = 1 << 30, best_pad = 1 << 30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
+  int best = step, best_tiles = 1 << 30, best_pad = 1 << 30;
+  for (int bn = 256; bn >= step; bn -= step) {
     if (plane_cols != N && span % bn != 0) continue;
     const int tiles = (span + bn - 1) / bn, pad = tiles * bn - span;
     if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best = bn; best_tiles = tiles; best_pad = pad; }
@@ -374,7 +375,7 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
     const actk_gemm_problem &p = pr[g];
     GemmProblemDev &d = P.p[g];
     const int pc = p.N / p.planes;
-    d.bn = gemm_pick_bn(p.N, pc);
+    d.bn = gemm_pick_bn(p.N, pc, p.n_peers > 0 ? 64 : 32);
     d.plane_cols = pc;
     d.M = p.M; d.N = p.N;
     d.epilogue = p.epilogue;

@@ -349,25 +349,27 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
             # scan launch shape, within fp32 re-association when a rank's few frames take the two-level scan instead
             same = bool(torch.equal(res["t1_y"], res["tN_y"]))
             diff = (res["t1_y"].float() - res["tN_y"].float()).abs().max()
-            if push:
-                same = same and bool(torch.equal(res["tN_y"], res["tP_y"]))    # same kernels, other transport
-        flag = torch.tensor([1 if same else 0], device=dev)
+            same_push = bool(torch.equal(res["tN_y"], res["tP_y"])) if push else True   # same kernels, other transport
+        flag = torch.tensor([1 if same else 0, 1 if same_push else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
         out[f"Bp{Bp}"] = {"ms_1gpu": res["t1"], "ms_Ngpu": res["tN"], "efficiency": res["t1"] / (world * res["tN"]),
                           "frames_per_rank": [hi - lo for lo, hi in call.plan(Bp).all_bounds()],
                           "gather_bytes_per_rank": Bp * L * d_model * x.element_size(),
-                          "bit_identical_to_one_gpu": bool(flag.item()), "max_abs_diff_vs_one_gpu": diff.item(),
+                          "bit_identical_to_one_gpu": bool(flag[0].item()), "max_abs_diff_vs_one_gpu": diff.item(),
                           "phases_ms": call.phase_ms(),
                           "tiles_per_rank": call.tiles}
         if push:   # fused out_proj + all-gather over NVLink peer memory (TMA stores into every rank's buffer)
             out[f"Bp{Bp}"]["fused_push"] = {"ms_Ngpu": res["tP"], "efficiency": res["t1"] / (world * res["tP"]),
-                                            "phases_ms": push.phase_ms()}
+                                            "phases_ms": push.phase_ms(),
+                                            "bit_identical_to_nccl_route": bool(flag[1].item())}
             push._peer.close()
         del x, idm, cd, res
     out["what"] = ("one call split batch-first (whole frames per rank), result all-gathered to every rank (NCCL over "
                    f"NVLink) inside the timed region; up to {args.strong_tiles} tiles per rank (>= 25 frames each) so the "
-                   "gather of tile i runs under the compute of tile i+1; efficiency = t1 / (N * tN)")
+                   "gather of tile i runs under the compute of tile i+1; efficiency = t1 / (N * tN).  fused_push: the "
+                   "out_proj kernel itself stores every output tile into all ranks' buffers over NVLink peer memory (TMA "
+                   "stores, no collective launch; a 4-byte all-reduce orders readers behind writers)")
     return out
 
 
