@@ -277,12 +277,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
         }
         __syncwarp();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader && col0 + cc * 64 < pr.plane_cols && row0 < pr.M) {
-          if (P.n_peers > 0) {      // the same staging tile goes to every rank's buffer: GEMM and all-gather in one kernel
-            for (int pe = 0; pe < P.n_peers; ++pe) gemm_tma_store_3d(&P.peer_c[pe], col0 + cc * 64, row0, plane, buf);
-          } else {
-            gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
+        if (leader) {
+          if (col0 + cc * 64 < pr.plane_cols && row0 < pr.M) {
+            if (P.n_peers > 0) {    // the same staging tile goes to every rank's buffer: GEMM and all-gather in one kernel
+              for (int pe = 0; pe < P.n_peers; ++pe) gemm_tma_store_3d(&P.peer_c[pe], col0 + cc * 64, row0, plane, buf);
+            } else {
+              gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
+            }
           }
+          // ONE group per chunk, also for a chunk that lies outside the output (empty group): the wait above counts
+          // groups, and a chunk without one would let the tile two chunks on overwrite a staging tile whose stores are
+          // still reading it (seen at 8 GPUs: the last-issued, slowest peer stores of the fused all-gather picked up the
+          // next tile's data)
           bulk_commit();
         }
       }

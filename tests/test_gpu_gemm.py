@@ -166,3 +166,25 @@ def test_layer_tensor_core_route_equals_torch_gemm_route(dtype):
         step = 2.0 ** -6 if dtype == torch.bfloat16 else 2.0 ** -9
         err = (got.float() - want.float()).abs()
         assert (err <= step * (1.0 + want.float().abs())).all(), (d_model, err.max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_gemm_fused_all_gather_stores_every_tile_to_every_target(dtype):
+    """The fused GEMM + all-gather epilogue on ONE GPU: eight 'rank' buffers that all live here.  N = 320 takes 192-column
+    tiles (store maps are 64 columns wide), so every second tile ends in a chunk that lies outside the output — the case
+    that once let a staging tile be overwritten while the last-issued stores were still reading it."""
+    from actalker_b200 import gemm
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 40000, 320, 640
+    a = torch.randn(M, K, generator=g).to(dtype).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype).cuda()
+    want = torch.empty(M, N, dtype=dtype, device="cuda")
+    gemm.run([gemm.Problem(a, w, want)])
+    bufs = [torch.full((3 + M, N), float("nan"), dtype=dtype, device="cuda") for _ in range(8)]
+    for _ in range(3):
+        gemm.run([gemm.Problem(a, w, None, peers=[b[3:].data_ptr() for b in bufs])])
+    torch.cuda.synchronize()
+    for i, b in enumerate(bufs):
+        assert torch.equal(b[3:], want), f"target {i}: {(b[3:] != want).sum().item()} elements differ"
+        assert torch.isnan(b[:3].float()).all()
+    _check(want.cpu(), _ref(a.cpu(), w.cpu(), dtype), dtype, "fused all-gather reference")
