@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kOpCh) selective_scan_kernel(const __grid_cons
 
   const bool live = tid < nch;
   const int ch = c0 + (live ? tid : 0);
-  ChannelScan<POWER_A> cs;
+  ChannelScan<POWER_A, sizeof(T) == 2> cs;   // 16-bit I/O: softplus without the small-argument series (scan_core.cuh)
   cs.init(a.A + (size_t)ch * kN, a.D ? a.D[ch] : 0.f, a.delta_bias ? a.delta_bias[ch] : 0.f);
 
   // Register-staged tile pipeline: every global load of tile i+1 is issued (as ~80 independent LDGs per thread)
