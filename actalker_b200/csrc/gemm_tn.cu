@@ -326,10 +326,16 @@ static GemmEncodeFn gemm_encode_fn() {
 // column-tile width: the fewest tiles of at most 256 columns, then the least padding; multiples of 32 (of 64 for the fused
 // all-gather, whose per-rank store maps are 64 columns wide); when the output is split into planes a tile must not
 // straddle two of them
+static int gemm_bn_cap() {   // tuning: ACTK_GEMM_BN_MAX=128|192|256 caps the column-tile width
+  const char *e = getenv("ACTK_GEMM_BN_MAX");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 64 && v <= 256) ? v / 32 * 32 : 256;
+}
+
 static int gemm_pick_bn(int N, int plane_cols, int step = 32) {
   const int span = plane_cols;                         // tiles are laid out per plane
   int best = step, best_tiles = 1 << 30, best_pad = 1 << 30;
-  for (int bn = 256; bn >= step; bn -= step) {
+  for (int bn = gemm_bn_cap() / step * step; bn >= step; bn -= step) {
     if (plane_cols != N && span % bn != 0) continue;
     const int tiles = (span + bn - 1) / bn, pad = tiles * bn - span;
     if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best = bn; best_tiles = tiles; best_pad = pad; }

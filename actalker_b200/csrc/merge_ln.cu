@@ -177,6 +177,145 @@ __global__ void __launch_bounds__(128, (VPL <= 4 && sizeof(T) == 2) ? ACTK_MERGE
   }
 }
 
+// merge_ln_kernel with WPR = 2 or 4 warps sharing a row: the UNet's wide layers (D = 1280 / 2560) would otherwise hold 5 / 10 vectors per
+// lane and tensor in registers (234 registers, two CTAs per SM: 1.9 TB/s at D = 2560, profiles/r02_merge_ln_wide_ncu.txt);
+// with the row split every width runs the 3-vector schedule of D = 640 and the statistics cross the warps through
+// shared memory.  Lane `lane` of part `part` owns vectors lane + 32 * (part + WPR * i).  (A separate kernel: folding
+// WPR = 1 into this body moved the D = 640 instantiation across the 80-register line of its 6-CTA launch bound.)
+template <typename T, int VPL, int WPR>
+__global__ void __launch_bounds__(128, (VPL <= 4 && sizeof(T) == 2) ? ACTK_MERGE_MINB - 1 : 1) merge_ln_split_kernel(const __grid_constant__ MergeParams P) {
+  const actk_merge_ln_args &a = P.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = WPR == 1 ? 0 : warp % WPR;
+  const long long rows = (long long)a.Bp * a.L;
+  const long long row_raw = WPR == 1 ? (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)
+                                     : (long long)blockIdx.x * (4 / WPR) + warp / WPR;
+  if (WPR == 1 && row_raw >= rows) return;
+  // WPR > 1: partner warps of a row must reach the barriers, so a row past the end recomputes the last one and stores nothing
+  const bool valid = WPR == 1 ? true : row_raw < rows;
+  const long long row = (WPR == 1 || valid) ? row_raw : rows - 1;
+  const int l = (int)(row % a.L);
+  const int D = a.D, nvec = D >> 3;
+  const size_t off = (size_t)row * D;
+  const size_t dir1 = (size_t)rows * D;   // ydir[1] - ydir[0]
+
+  // The row flags are uniform over the warp, so every load address is known up front: all 16-byte loads of a chunk
+  // of up to 4 vectors per lane (x 2 branches x 2 directions) are issued before any arithmetic — the kernel is a
+  // pure HBM stream and was latency-bound with two loads in flight per lane (186 -> see DESIGN.md us at config 2).
+  bool sel[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) sel[br] = br < a.n_branches && a.selected[br][l] != 0;
+  constexpr int CH = VPL < 4 ? VPL : 4;
+  float x[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i0 = 0; i0 < VPL; i0 += CH) {
+    Raw8<T> raw[CH][2][2];
+#pragma unroll
+    for (int ii = 0; ii < CH; ++ii) {
+      const int v = lane + 32 * (part + WPR * (i0 + ii));
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        if (v < nvec && br < a.n_branches) {
+          const T *p = (sel[br] ? (const T *)a.ydir[br] : (const T *)a.xz[br]) + off + 8 * v;
+          raw[ii][br][0] = ldraw8(p);
+          if (sel[br]) raw[ii][br][1] = ldraw8(p + dir1);
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < CH; ++ii) {
+      const int i = i0 + ii, v = lane + 32 * (part + WPR * i);
+      if (v < nvec) {
+        float acc[8];
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          if (br >= a.n_branches) break;
+          float t[8];
+          unpack8<T>(raw[ii][br][0], t);
+          if (sel[br]) {
+            float g[8];
+            unpack8<T>(raw[ii][br][1], g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] + g[e]);
+            if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
+              const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
+      }
+    }
+  }
+  if (!a.layernorm) {   // channel-sharded path: emit the merged sums, LayerNorm follows the all-gather
+    if (a.n_peers > 0) {
+      // fused push all-gather: this rank's slice goes straight into every rank's gather buffer over NVLink (16-byte
+      // peer stores), in the (part, row, slice) layout gathered_ln_kernel reads — no separate collective launch
+      const size_t poff = ((size_t)a.my_part * rows + row) * D;
+      if (!valid) return;
+      for (int p = 0; p < a.n_peers; ++p) {
+        T *dst = (T *)a.peer_out[p] + poff;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * (part + WPR * i);
+          if (v < nvec) store8(dst + 8 * v, x[i]);
+        }
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * (part + WPR * i);
+      if (v < nvec && valid) store8((T *)a.out + off + 8 * v, x[i]);
+    }
+    return;
+  }
+  __shared__ float red_sum[WPR > 1 ? 4 : 1], red_sq[WPR > 1 ? 4 : 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (WPR > 1) {     // the row's parts meet in shared memory
+    if (lane == 0) red_sum[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < WPR; ++j) sum += red_sum[warp / WPR * WPR + j];
+  }
+  const float mean = sum / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    if (lane + 32 * (part + WPR * i) < nvec)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { float d = x[i][e] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (WPR > 1) {
+    if (lane == 0) red_sq[warp] = sq;
+    __syncthreads();
+    sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < WPR; ++j) sq += red_sq[warp / WPR * WPR + j];
+  }
+  const float rstd = rsqrtf(sq / D + a.eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * (part + WPR * i);
+    if (v < nvec && valid) {
+      float g[8], bt[8], o[8];
+      load8((const T *)a.gamma + 8 * v, g);
+      load8((const T *)a.beta + 8 * v, bt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf((x[i][e] - mean) * rstd, g[e], bt[e]);
+      store8((T *)a.out + off + 8 * v, o);
+    }
+  }
+}
+
 // LayerNorm over channel slices gathered from P ranks: in (P, rows, Ds) -> out (rows, P*Ds).
 // One warp per row; slice p of a row sits at in + (p*rows + row)*Ds (the layout NCCL all-gather produces).
 template <typename T, int VPL>
@@ -244,13 +383,16 @@ template <typename T>
 int launch_merge(const actk_merge_ln_args *a, cudaStream_t stream) {
   MergeParams P;
   P.a = *a;
-  const int vpl = ((a->D >> 3) + 31) / 32;
+  const int nvec = a->D >> 3;
   const long long rows = (long long)a->Bp * a->L;
-  const unsigned grid = (unsigned)((rows + 3) / 4);
-  if (vpl <= 4) merge_ln_kernel<T, 4><<<grid, 128, 0, stream>>>(P);
-  else if (vpl <= 8) merge_ln_kernel<T, 8><<<grid, 128, 0, stream>>>(P);
-  else if (vpl <= 16) merge_ln_kernel<T, 16><<<grid, 128, 0, stream>>>(P);
-  else merge_ln_kernel<T, 32><<<grid, 128, 0, stream>>>(P);
+  // warps per row: as few as keep <= 4 vectors per lane (D <= 1024: 1, <= 2048: 2, else 4)
+  const int wpr = nvec <= 128 ? 1 : (nvec <= 256 ? 2 : 4);
+  const int vpl = (nvec + 32 * wpr - 1) / (32 * wpr);
+  const unsigned grid = (unsigned)((rows * wpr + 3) / 4);
+  if (wpr == 1) merge_ln_kernel<T, 4><<<grid, 128, 0, stream>>>(P);
+  else if (wpr == 2) merge_ln_split_kernel<T, 4, 2><<<grid, 128, 0, stream>>>(P);
+  else if (vpl <= 4) merge_ln_split_kernel<T, 4, 4><<<grid, 128, 0, stream>>>(P);
+  else merge_ln_split_kernel<T, 8, 4><<<grid, 128, 0, stream>>>(P);   // D up to 8192
   ACTK_CUDA_OK(cudaGetLastError());
   return ACTK_OK;
 }

@@ -81,7 +81,7 @@ def _ours(kw, sd, dtype):
 @pytest.mark.parametrize("launch", ["default", "chain", "two_level"])
 @pytest.mark.parametrize("mkind", ["ones", "rects"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("width", [(640, 36, 2), (1280, 18, 4)])
+@pytest.mark.parametrize("width", [(640, 36, 2), (1280, 18, 4), (640, 3, 1)])   # last: 9 rows, odd: the split merge's row tail
 def test_layer_matches_oracle_at_unet_widths(width, dtype, mkind, launch):
     """d_model 640 (36x36 tokens, D = 1280, dt_rank 40 -> rank pad 48) and 1280 (18x18, D = 2560, dt_rank 80) against the
     oracle, fp32 / bf16 / fp16, all-ones masks and a mouth / upper-face rectangle pair, three launch shapes."""
