@@ -1,19 +1,27 @@
-set -x
-cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out/r2
-python bench.py > gpurun_out/r2/bench_init.json 2> gpurun_out/r2/bench_init.err
-python bench.py --params trained --no-cpu-baseline > gpurun_out/r2/bench_trained.json 2>/dev/null
-python bench.py --params s4d --no-cpu-baseline > gpurun_out/r2/bench_s4d.json 2>/dev/null
-python bench.py --cfg 4 --no-cpu-baseline > gpurun_out/r2/bench_cfg4.json 2>/dev/null
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2/bench_reference.json 2>/dev/null
-ACTK_FUSE_DT=1 python bench.py --no-cpu-baseline > gpurun_out/r2/bench_fused_dt.json 2>/dev/null
-ACTK_FUSE_LN_OUT=1 python bench.py --no-cpu-baseline > gpurun_out/r2/bench_fused_lnout.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:masked_scan -s 6 -c 1 -o gpurun_out/r2/masked_scan_general python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:masked_scan -s 6 -c 1 -o gpurun_out/r2/masked_scan_power python bench.py --steps 2 --warmup 3 --no-cpu-baseline --params s4d > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:merge_ln -s 3 -c 1 -o gpurun_out/r2/merge_ln python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ACTK_FUSE_DT=1 ncu --set full --clock-control none --import-source on -k regex:masked_scan -s 6 -c 1 -o gpurun_out/r2/masked_scan_fused_dt python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-python tools/bench_configs.py > gpurun_out/r2/configs_3_5.jsonl 2>/dev/null
-python tools/bench_latency.py > gpurun_out/r2/latency_graph.jsonl 2>/dev/null
-python tools/bench_operator.py > gpurun_out/r2/operator.txt 2>/dev/null
-ls -la gpurun_out/r2
+#!/bin/bash
+# The round's bench records on one B200 (no profiler): default line, parameter variants, CFG x4, the cuBLAS-route comparison,
+# the opt-in fusions, a short reference arm, configs 3 / 5 and the operator seam.  tools/profile_round2.sh is the ncu pass.
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out/${1:-r2rec}
+mkdir -p "$O"
+python bench.py > "$O/bench_init.json" 2> "$O/bench_init.err"; echo "init_rc=$?"
+python bench.py --params trained --no-cpu-baseline > "$O/bench_trained.json" 2>/dev/null; echo "trained_rc=$?"
+python bench.py --params s4d --no-cpu-baseline > "$O/bench_s4d.json" 2>/dev/null; echo "s4d_rc=$?"
+python bench.py --cfg 4 --no-cpu-baseline > "$O/bench_cfg4.json" 2>/dev/null; echo "cfg4_rc=$?"
+ACTK_TC_GEMM=0 python bench.py --no-cpu-baseline > "$O/bench_cublas_route.json" 2>/dev/null; echo "cublas_rc=$?"
+ACTK_FUSE_DT=1 python bench.py --no-cpu-baseline > "$O/bench_fused_dt.json" 2>/dev/null; echo "fused_dt_rc=$?"
+ACTK_FUSE_LN_OUT=1 python bench.py --no-cpu-baseline > "$O/bench_fused_lnout.json" 2>/dev/null; echo "fused_ln_rc=$?"
+python bench.py --dtype f16 --no-cpu-baseline > "$O/bench_f16.json" 2>/dev/null; echo "f16_rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > "$O/bench_reference.json" 2>/dev/null; echo "reference_rc=$?"
+python tools/bench_configs.py > "$O/configs_3_5.jsonl" 2>/dev/null; echo "configs_rc=$?"
+python tools/bench_operator.py > "$O/operator.txt" 2>/dev/null; echo "operator_rc=$?"
+python tools/bench_latency.py > "$O/latency_graph.jsonl" 2>/dev/null
+python - "$O" <<'PY'
+import json,sys,glob,os
+for f in sorted(glob.glob(os.path.join(sys.argv[1],"bench_*.json"))):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        r=d.get("roofline",{})
+        print(os.path.basename(f).ljust(28), "ms/step", round(d["ms_per_step"],3), "value", round(d["value"],5), "scan", round(r.get("kernel_ms",0),3), "frac", round(r.get("frac",0),4), "e2e", round(d["e2e"]["ms_per_step"],3) if "ms_per_step" in d.get("e2e",{}) else "", d.get("same_config",""))
+    except Exception as e: print(f, "ERR", e)
+PY
