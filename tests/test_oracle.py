@@ -233,7 +233,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     # two frames fit the time budget: every step is the full workload, and the config block is the GPU arm's own
     assert d["same_config"] is True and d["frames_per_step"] == 2 and "sample" not in d["config"]
     assert set(d["config"]) == {"workload", "tokens_per_step_per_gpu", "l2", "a_kind", "parallelism"}
-    assert d["full_workload_estimate"]["ms_per_step"] > 0
+    assert "full_workload_estimate" not in d              # only a sampled run extrapolates
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames per step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Gtokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
