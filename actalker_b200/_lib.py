@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
@@ -40,7 +40,7 @@ class ScanArgs(C.Structure):
 class BranchArgs(C.Structure):
     _fields_ = [("xz", _vp), ("tail", _vp), ("xdbl", _vp), ("xdbl_tail", _vp), ("delta", _vp),
                 ("delta_tail", _vp), ("idx", _vp), ("A", _vp), ("Dskip", _vp), ("dt_bias", _vp), ("ydir", _vp),
-                ("n_sel", _i), ("n_tail", _i), ("a_kind", _i), ("w_dt", _vp)]
+                ("n_sel", _i), ("n_tail", _i), ("a_kind", _i), ("w_dt", _vp), ("bc32", _vp), ("bc32_tail", _vp)]
 
 
 class MaskedScanArgs(C.Structure):
@@ -59,7 +59,8 @@ class MergeLnArgs(C.Structure):
 
 class GemmProblem(C.Structure):
     _fields_ = [("a", _vp), ("w", _vp), ("c", _vp), ("lda", _ll), ("ldw", _ll), ("ldc", _ll), ("plane_stride", _ll),
-                ("M", _i), ("N", _i), ("K", _i), ("planes", _i), ("epilogue", _i), ("peer_c", _vp * 8), ("n_peers", _i)]
+                ("M", _i), ("N", _i), ("K", _i), ("planes", _i), ("epilogue", _i), ("peer_c", _vp * 8), ("n_peers", _i),
+                ("c_f32", _vp), ("ldc_f32", _ll), ("f32_cols", _i)]
 
 
 GEMM_MAX_PROBLEMS = 4

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libactalker_b200.so")
 # scan has one translation unit per dt-rank slab count, so that the long template instantiations build in parallel.
 SOURCES = [("api.cu", (), ""), ("masked_scan.cu", (), ""),
            ("masked_scan_ks0.cu", (), ""), ("masked_scan_ks2.cu", (), ""), ("masked_scan_ks3.cu", (), ""),
-           ("masked_scan_ks5.cu", (), ""), ("ln_outproj.cu", (), ""), ("gemm_tn.cu", (), ""),
+           ("masked_scan_ks5.cu", (), ""), ("masked_scan_lean.cu", (), ""), ("ln_outproj.cu", (), ""), ("gemm_tn.cu", (), ""),
            ("selective_scan.cu", (), ""), ("merge_ln.cu", (), "")] + \
           [(src, (f"ACTK_TU_DTYPE={n}",), f"_t{n}") for src in ("selective_scan.cu", "merge_ln.cu") for n in (0, 1, 2)]
 NVCC_FLAGS = [

@@ -108,6 +108,21 @@ __device__ __forceinline__ float softplus20_io16(float x) {
   float r = lg2(1.0f + e) * kLn2;
   return x > 20.0f ? x : r;
 }
+// One MUFU instead of two: softplus(x) = max(x, 0) + log1p(e), e = exp(-|x|) in (0, 1], with log1p(e) = e * q(e), q a
+// degree-5 minimax polynomial of log1p(e)/e on [0, 1] constrained to q(0) = 1 (max relative error 9.6e-6 on dt over the
+// whole range — six times tighter than softplus20_io16 at small dt — and x > 20 returns x exactly: log1p(e^-20) is below
+// half an ulp of 20).  The scan is bound by the MUFU pipe (16 per channel-step, ~80 % busy) while the FMA pipe has slack:
+// this trades the lg2 for five FFMA + one FMUL.  16-bit I/O only, like softplus20_io16.
+__device__ __forceinline__ float softplus20_io16_poly(float x) {
+  const float e = ex2(-fabsf(x) * kLog2e);
+  float q = -0.02473430335521698f;
+  q = fmaf(q, e, 0.10359206795692444f);
+  q = fmaf(q, e, -0.21240372955799103f);
+  q = fmaf(q, e, 0.3262259364128113f);
+  q = fmaf(q, e, -0.49953946471214294f);
+  q = fmaf(q, e, 1.0f);
+  return fmaf(q, e, fmaxf(x, 0.0f));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + ex2(-x * kLog2e)); }
 
 // ----------------------------------------------------------------------------- packed fp32x2 (sm_100+)
@@ -194,7 +209,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 // The wait sleeps in hardware until the phase completes or the hint expires; the default hint is so short
 // that an idle producer warp re-polls every ~45 cycles and takes issue slots from the compute warps.
-constexpr uint32_t kSuspendHintNs = 20000;
+#ifndef ACTK_SUSPEND_NS
+#define ACTK_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kSuspendHintNs = ACTK_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t"

@@ -44,6 +44,8 @@ constexpr int kMaxGemmProblems = ACTK_GEMM_MAX_PROBLEMS;
 struct GemmProblemDev {
   CUtensorMap a, w, c;   // c: 64-column store boxes (SWIZZLE_128B)
   CUtensorMap c32;       // 32-column store boxes (SWIZZLE_64B) for the last chunk of a tile whose width is 32 mod 64
+  CUtensorMap cf32;      // fp32 side output: boxes of 32 fp32 columns x 128 rows (SWIZZLE_128B)
+  int f32_cols;          // leading output columns that are ALSO written, widened from the rounded result, to c_f32 (0 / 32 / 64)
   int tiles_per_plane;
   int n_tiles;        // column tiles per row tile
   int k_slabs;
@@ -120,6 +122,13 @@ __device__ __forceinline__ void gemm_tmem_ld16(uint32_t taddr, uint32_t *r) {   
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void gemm_tmem_wait16(uint32_t *r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void gemm_tmem_wait32(uint32_t *r) {   // ties all 32 registers to the wait
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
@@ -161,6 +170,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     mbar_fence_init();
     for (int g = 0; g < P.n_problems; ++g) {
       tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); tmap_prefetch(&P.p[g].c32);
+      if (P.p[g].f32_cols) tmap_prefetch(&P.p[g].cf32);
     }
     for (int pe = 0; pe < P.n_peers; ++pe) tmap_prefetch(&P.peer_c[pe]);
   }
@@ -238,12 +248,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       gemm_bar_wait(tfull_bar + 8 * b, ub & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int nchunks = (pr.bn + 63) >> 6;
-      for (int hc = 0; hc < MH * nchunks; ++hc, ++chunk_count) {
+      // fp32 side output (x_proj: the scan reads B|C as fp32 without widening them per tile): the leading f32_cols
+      // columns of the first column tile go out a second time, as the ROUNDED result widened to fp32, in extra chunks of
+      // 32 fp32 columns (128-byte staging rows, the same swizzle and the same staging-tile rotation as the 16-bit chunks)
+      const int nf32 = (MH == 1 && n == 0) ? (pr.f32_cols >> 5) : 0;
+      for (int hc = 0; hc < MH * nchunks + nf32; ++hc, ++chunk_count) {
+        const uint32_t buf = epi_base + (chunk_count % (uint32_t)P.epi_bufs) * kEpiBufBytes;
+        if (hc >= MH * nchunks) {
+          const int v = hc - MH * nchunks;      // fp32 columns [32 v, 32 v + 32): every warp converts 16 of them for its rows
+          const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256;
+          uint32_t f16r[16];
+          gemm_tmem_ld16(trow + v * 32 + h * 16, f16r);
+          gemm_tmem_wait16(f16r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f16r[i] = __float_as_uint(IO<T>::rnd(__uint_as_float(f16r[i])));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = buf + (uint32_t)r * 128 + (uint32_t)(((4 * h + j) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(f16r[4 * j]), "r"(f16r[4 * j + 1]),
+                         "r"(f16r[4 * j + 2]), "r"(f16r[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          if (leader) {
+            if (P.epi_bufs >= 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
+          __syncwarp();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            if (m * kBM < pr.M) gemm_tma_store_3d(&pr.cf32, v * 32, m * kBM, 0, buf);
+            bulk_commit();
+          }
+          continue;
+        }
         const int hh = MH == 2 ? (hc >= nchunks ? 1 : 0) : 0, cc = hc - hh * nchunks;   // row half, 64-column chunk
         const int row0 = (m * MH + hh) * kBM;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256 + hh * P.acc_hstride;
         const int width = pr.bn - cc * 64 >= 64 ? 64 : 32;          // bn is a multiple of 32
-        const uint32_t buf = epi_base + (chunk_count % (uint32_t)P.epi_bufs) * kEpiBufBytes;
         if (h * 32 < width) {
           uint32_t v32[32];
           gemm_tmem_ld16(trow + cc * 64 + h * 32, v32);
@@ -360,6 +401,13 @@ static const char *gemm_check(const actk_gemm_problem &p, int es) {
   if ((p.lda * es) % 16 || (p.ldw * es) % 16 || (p.ldc * es) % 16 || (p.plane_stride * es) % 16) return "row pitch not a multiple of 16 bytes";
   if ((reinterpret_cast<uintptr_t>(p.a) | reinterpret_cast<uintptr_t>(p.w) | (p.n_peers ? 0 : reinterpret_cast<uintptr_t>(p.c))) & 15)
     return "pointer not aligned to 16 bytes";
+  if (p.f32_cols != 0) {
+    if (!p.c_f32) return "NULL pointer (fp32 side output)";
+    if ((p.f32_cols != 32 && p.f32_cols != 64) || p.f32_cols > p.N || p.planes != 1 || p.n_peers != 0)
+      return "the fp32 side output covers the first 32 or 64 columns of a one-plane product";
+    if (p.ldc_f32 < p.f32_cols || (p.ldc_f32 * 4) % 16 || (reinterpret_cast<uintptr_t>(p.c_f32) & 15))
+      return "fp32 side output: row pitch / pointer not a multiple of 16 bytes";
+  }
   return nullptr;
 }
 
@@ -425,6 +473,17 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (peer %d) failed with CUresult %d", pe, (int)r);
       }
+    }
+    d.f32_cols = 0;
+    if (p.f32_cols != 0) {   // fp32 side output (M, f32_cols): boxes of 32 columns x 128 rows
+      if (MH != 1 || d.bn < p.f32_cols) ACTK_FAIL(ACTK_ERR_UNSUPPORTED, "gemm_tn: the fp32 side output needs 128-row tiles of at least %d columns", p.f32_cols);
+      d.f32_cols = p.f32_cols;
+      cuuint64_t dims[3] = {(cuuint64_t)p.f32_cols, (cuuint64_t)p.M, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)p.ldc_f32 * 4, (cuuint64_t)p.ldc_f32 * 4 * p.M};
+      cuuint32_t box[3] = {32u, (cuuint32_t)kBM, 1};
+      CUresult r = fn(&d.cf32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.c_f32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (fp32 side output of problem %d) failed with CUresult %d", g, (int)r);
     }
     for (int narrow = 0; narrow < 2 && p.n_peers == 0; ++narrow) {   // C (plane_cols, M, planes): 128-row store boxes of 64 / 32 columns
       cuuint64_t dims[3] = {(cuuint64_t)pc, (cuuint64_t)p.M, (cuuint64_t)p.planes};

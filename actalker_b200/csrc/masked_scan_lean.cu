@@ -1,0 +1,309 @@
+// Lean form of the fused masked bidirectional selective scan for the launches the shipped pipeline makes: 16-bit
+// activations, all-ones region masks (idx[p] == p, Inference.py:545-546), D a multiple of 64, delta tensors given, and
+// the B|C columns of x_dbl also available as fp32 (the x_proj launch writes them: actk_gemm_problem.c_f32).
+// Same entry point (actk_masked_scan_fwd picks it), same reference lines as masked_scan_kernel.cuh
+// (src/models/base/mamba_layer.py:1963-1970 gather / tail concat / scatter, :1505-1548 forward_core, :1532-1538 the scan),
+// the same ChannelScan arithmetic in the same order — results are bit-identical to the general kernel.
+//
+// What is different is everything AROUND the 16-step hot loops, which ncu's per-instruction samples put at a quarter of
+// the general kernel's warp time (profiles/r02_scan_instruction_accounting.txt: ~190 instructions per warp and tile of
+// tile geometry, B|C widening, CTA barrier and TMA issue; 2.8 % of all samples on the barrier alone):
+//   * the two warps of a CTA (32 channels each) never meet at a CTA barrier inside the tile loop.  Ring slots are
+//     handed back through `empty` mbarriers (one arrival per warp), tiles arrive on `full` mbarriers (TMA transaction
+//     bytes), and each warp returns ITS half of the y tile with its own TMA store from its own double buffer;
+//   * B|C arrive as fp32 straight from the tensor map: no per-tile widening pass, no second shared copy;
+//   * the refill of a slot is issued two tiles ahead by the warps in turn (even tiles: warp 0, odd tiles: warp 1), so
+//     the slot it needs was released a whole tile ago and the elected lane practically never waits;
+//   * tile geometry is two comparisons: with idx == iota the fast tiles (16 consecutive latent rows) are one contiguous
+//     range of tile numbers per direction; only the id / condition tail and the partial last tile (2-3 tiles of a
+//     sequence) take the ragged path, which the refilling warp serves alone with cp.async.
+#include <cuda.h>
+
+#include "masked_scan_types.cuh"
+
+namespace actk {
+
+template <typename T>
+struct alignas(128) LeanStage {
+  T u[kT][kCh];
+  T dt[kT][kCh];
+  float bc[kT][2 * kN];
+};
+
+__device__ __forceinline__ void cp_async_arrive_inc(uint64_t *bar) {   // tracked cp.asyncs of this thread; net-zero on the count
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Single-lane work of the tile loop is PREDICATED inside the asm (`on` is non-zero in one lane of the warp) instead of
+// sitting in an `if (lane == 0)`: a lane-dependent branch in the tile loop left lane 0 and lanes 1-31 of a warp running
+// whole tiles as two separate groups (ncu: the 8-step loops executed 4.6 % more often than there are tiles, BRA.DIV taken
+// at every __syncwarp), which an issue-bound kernel pays in full.
+__device__ __forceinline__ void lean_issue_loads(uint32_t on, uint64_t *bar, uint32_t bytes, void *dst_dt, const void *map_dt,
+                                                 int c0_dt, void *dst_u, const void *map_u, int c0_u, void *dst_bc,
+                                                 const void *map_bc, int c0_bc, int row, int b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %0, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %2;\n\t"
+      "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%3], [%4, {%5, %12, %13}], [%1];\n\t"
+      "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%6], [%7, {%8, %12, %13}], [%1];\n\t"
+      "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%9], [%10, {%11, %12, %13}], [%1];\n\t"
+      "}" ::"r"(on), "r"(smem_u32(bar)), "r"(bytes), "r"(smem_u32(dst_dt)), "l"(map_dt), "r"(c0_dt), "r"(smem_u32(dst_u)),
+      "l"(map_u), "r"(c0_u), "r"(smem_u32(dst_bc)), "l"(map_bc), "r"(c0_bc), "r"(row), "r"(b)
+      : "memory");
+}
+// release of a ring slot + this warp's y tile: arrive on `empty`, TMA store, commit; then (all lanes, a no-op for lanes
+// that never committed a group) wait until at most one store is still reading shared memory
+__device__ __forceinline__ void lean_release_and_store(uint32_t on, uint64_t *empty, const void *map_y, int c0, int row, int c2,
+                                                       const void *src) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %0, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%1];\n\t"
+      "@p cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%2, {%3, %4, %5}], [%6];\n\t"
+      "cp.async.bulk.commit_group;\n\t"
+      "cp.async.bulk.wait_group.read 1;\n\t"
+      "}" ::"r"(on), "r"(smem_u32(empty)), "l"(map_y), "r"(c0), "r"(row), "r"(c2), "r"(smem_u32(src))
+      : "memory");
+}
+__device__ __forceinline__ void lean_arrive(uint32_t on, uint64_t *bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %0, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%1];\n\t"
+      "}" ::"r"(on), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// S ring slots; tiles are requested S - 2 tiles ahead (the slot being refilled was released one whole tile ago).
+// CHAIN: chained chunks drawn from an atomic counter (masked_scan_kernel.cuh MODE 2, same workspace protocol).
+template <typename T, bool POWER_A, bool CHAIN, int S>
+__global__ void __launch_bounds__(kCh) masked_scan_lean_kernel(const __grid_constant__ MaskedParams<T> P,
+                                                               const __grid_constant__ MaskedMaps M) {
+  static_assert(sizeof(T) == 2, "lean scan: 16-bit activations");
+  constexpr int kG = S == 4 ? ACTK_LEAN_GROUP : kGroup;
+  constexpr int LA = S - 2;              // lookahead in tiles
+  constexpr int kW = 32;                 // channels per warp
+  __shared__ LeanStage<T> st[S];
+  __shared__ alignas(128) T ybuf[2][2][kT][kW];   // [warp][tile parity][row][channel of the warp]
+  __shared__ alignas(8) uint64_t full_bar[S];
+  __shared__ alignas(8) uint64_t empty_bar[S];
+  __shared__ int ticket_s;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const uint32_t lane0 = lane == 0 ? 1u : 0u;
+  int bx, b, zi, seg = 0, q = 0, nseg = 1;
+  if (CHAIN) {
+    nseg = P.nseg;
+    if (tid == 0) ticket_s = atomicAdd(P.chain_ctr, 1);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (CHAIN) {
+    const int ticket = ticket_s;
+    seg = ticket / P.nq;
+    q = ticket - seg * P.nq;
+    bx = q % P.nblk;
+    b = (q / P.nblk) % P.Bp;
+    zi = q / (P.nblk * P.Bp);
+  } else {
+    bx = blockIdx.x; b = blockIdx.y; zi = blockIdx.z;
+  }
+  const int d0 = bx * kCh;
+  const int bi = P.first_branch + (zi >> 1);
+  const int k = zi & 1;
+  const BranchDev<T> &br = P.br[bi];
+  const BranchMaps &maps = M.m[bi];
+  const int n_sel = br.n_sel, n_tail = br.n_tail;
+  const int Lp = n_sel + n_tail;
+  const int D = P.D, L = P.L;
+  const int ntiles = (Lp + kT - 1) / kT;
+  const int seg_tiles = (ntiles + nseg - 1) / nseg;
+  const int t_begin = min(seg * seg_tiles, ntiles), t_end = min(t_begin + seg_tiles, ntiles);
+  // fast tiles (16 rows, all of them selected latent tokens): [f_lo, f_hi) in tile numbers of this direction
+  const int f_lo = k == 0 ? 0 : (n_tail + kT - 1) / kT;
+  const int f_hi = k == 0 ? n_sel / kT : Lp / kT;
+  // sequence position (== latent row) held by shared-memory row 0 of tile t
+  auto first_row = [&](int t) { return k == 0 ? t * kT : Lp - kT - t * kT; };
+
+  // Tile t -> its ring slot.  Fast: the elected lane waits for the slot's release, arms the barrier with the byte count
+  // and issues three tensor-map loads.  Ragged: the whole warp gathers 16-byte pieces (u, delta, fp32 B|C rows of the
+  // valid positions) with cp.async tracked by the same barrier, then one plain arrival.
+  auto issue_tile = [&](int t) {
+    const int tr = t - t_begin, sn = tr % S, use = tr / S;
+    LeanStage<T> &sg = st[sn];
+    uint64_t *bar = &full_bar[sn];
+    const int l_first = first_row(t);
+    if (t >= f_lo && t < f_hi) {
+      if (use > 0) mbar_wait(&empty_bar[sn], (use - 1) & 1);      // all lanes: the outcome is the same for every lane
+      lean_issue_loads(lane0, bar, (uint32_t)sizeof(LeanStage<T>), &sg.dt[0][0], &maps.delta, k * D + d0, &sg.u[0][0], &maps.xz, d0,
+                       &sg.bc[0][0], &maps.bc32, k * 2 * kN, l_first, b);
+    } else {
+      if (use > 0) mbar_wait(&empty_bar[sn], (use - 1) & 1);
+      const int nrows = min(kT, Lp - t * kT);
+      const int l_lo = k == 0 ? t * kT : Lp - t * kT - nrows;
+      for (int id = lane; id < nrows * 24; id += 32) {
+        const int jj = id / 24, pc = id - jj * 24;
+        const int l = l_lo + jj, j = l - l_first;
+        const bool sel = l < n_sel;
+        const size_t tok = sel ? (size_t)b * n_sel + l : (size_t)b * n_tail + (l - n_sel);
+        if (pc < 8) {
+          const T *src = (sel ? br.xz + ((size_t)b * L + l) * D : br.tail + tok * D) + d0;
+          cp_async16(&sg.u[j][pc * 8], src + pc * 8);
+        } else if (pc < 16) {
+          const T *src = (sel ? br.delta : br.delta_tail) + (tok * 2 + k) * D + d0;
+          cp_async16(&sg.dt[j][(pc - 8) * 8], src + (pc - 8) * 8);
+        } else {
+          const float *src = (sel ? br.bc32 : br.bc32_tail) + tok * (4 * kN) + k * 2 * kN;
+          cp_async16(&sg.bc[j][(pc - 16) * 4], src + (pc - 16) * 4);
+        }
+      }
+      cp_async_arrive_inc(bar);
+      __syncwarp();
+      lean_arrive(lane0, bar);
+    }
+  };
+
+  const int ch = k * D + d0 + tid;
+  ChannelScan<POWER_A, true> cs;
+  // the first tiles are requested before the parameters are read and before a chained chunk waits for its predecessor
+  for (int t = t_begin; t < min(t_begin + LA, t_end); ++t) {
+#ifdef ACTK_LEAN_ONE_ISSUER
+    if (w == 0) issue_tile(t);
+#else
+    if (w == ((t - t_begin) & 1)) issue_tile(t);
+#endif
+  }
+  cs.init(br.A + (size_t)ch * kN, br.Dskip[ch], br.dt_bias[ch]);
+  if (tid == 0) { tmap_prefetch(&maps.ydir32); }
+
+  if (CHAIN && seg > 0) {
+    if (tid == 0) {   // acquire: the previous chunk of this sequence has published its state
+      int done;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(P.chain_flag + q) : "memory");
+        if (done < seg) __nanosleep(ACTK_CHAIN_POLL_NS);
+      } while (done < seg);
+    }
+    __syncthreads();
+    const float4 *h0 = reinterpret_cast<const float4 *>(P.chain_state + ((size_t)q * kCh + tid) * kN);
+#pragma unroll
+    for (int j = 0; j < kN / 4; ++j) {
+      const float4 v = __ldcg(h0 + j);
+      cs.h[2 * j] = pk(v.x, v.y);
+      cs.h[2 * j + 1] = pk(v.z, v.w);
+    }
+  }
+
+  T *ydst = br.ydir + ((size_t)k * P.Bp + b) * L * D + d0 + w * kW;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int tr = t - t_begin, s = tr % S;
+#ifdef ACTK_LEAN_ONE_ISSUER
+    if (t + LA < t_end && w == 0) issue_tile(t + LA);
+#else
+    if (t + LA < t_end && w == (tr & 1)) issue_tile(t + LA);
+#endif
+    mbar_wait(&full_bar[s], (tr / S) & 1);
+    __syncwarp();
+    const T *us = &st[s].u[0][tid];
+    const T *ds = &st[s].dt[0][tid];
+    const float *bcs = &st[s].bc[0][0];
+    T *ys = &ybuf[w][tr & 1][0][lane];
+    const bool fast = t >= f_lo && t < f_hi;
+    if (fast) {
+      // smem row of step r: r (direction 0) or 15 - r (direction 1); kG steps are software-pipelined
+      if (k == 0) {
+#pragma unroll 1
+        for (int r0 = 0; r0 < kT; r0 += kG) {
+          const T *u0 = us + r0 * kCh, *dl0 = ds + r0 * kCh;
+          const float *b0 = bcs + r0 * 2 * kN;
+          T *y0 = ys + r0 * kW;
+          cs.template run<kG, true>([&](int i) { return IO<T>::ld(u0 + i * kCh); },
+                                    [&](int i) { return IO<T>::ld(dl0 + i * kCh); },
+                                    [&](int i) { return b0 + i * 2 * kN; },
+                                    [&](int i, float y) { IO<T>::st(y0 + i * kW, y); });
+        }
+      } else {
+#pragma unroll 1
+        for (int r0 = 0; r0 < kT; r0 += kG) {
+          const int j0 = kT - 1 - r0;
+          const T *u0 = us + j0 * kCh, *dl0 = ds + j0 * kCh;
+          const float *b0 = bcs + j0 * 2 * kN;
+          T *y0 = ys + j0 * kW;
+          cs.template run<kG, true>([&](int i) { return IO<T>::ld(u0 - i * kCh); },
+                                    [&](int i) { return IO<T>::ld(dl0 - i * kCh); },
+                                    [&](int i) { return b0 - i * 2 * kN; },
+                                    [&](int i, float y) { IO<T>::st(y0 - i * kW, y); });
+        }
+      }
+      fence_proxy_async();   // this lane's y values are visible to the TMA store below
+      __syncwarp();
+      // one lane: this warp has read the slot; its y tile leaves; the store of the previous tile has read ybuf[w][(tr + 1) & 1]
+      lean_release_and_store(lane0, &empty_bar[s], &maps.ydir32, d0 + w * kW, first_row(t), k * P.Bp + b, &ybuf[w][tr & 1][0][0]);
+      __syncwarp();
+    } else {
+      const int nrows = min(kT, Lp - t * kT);
+      const int l_lo = k == 0 ? t * kT : Lp - t * kT - nrows;
+      const int l_first = first_row(t);
+      for (int r = 0; r < nrows; ++r) {
+        const int j = k ? kT - 1 - r : r;
+        const float y = cs.template step<true>(IO<T>::ld(us + j * kCh), IO<T>::ld(ds + j * kCh), bcs + j * 2 * kN);
+        IO<T>::st(ys + j * kW, y);
+      }
+      __syncwarp();
+      lean_arrive(lane0, &empty_bar[s]);
+      bulk_wait_read<0>();            // no store is sent for this tile: the buffer of the next one must be free all the same
+      // rows of selected latent tokens (none for pure tail tiles) go out with 128-bit stores: 4 pieces per 64-byte row
+      for (int id = lane; id < kT * 4; id += 32) {
+        const int jj = id >> 2, pc = id & 3, l = l_lo + jj;
+        if (jj < nrows && l < n_sel) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(&ybuf[w][tr & 1][l - l_first][pc * 8]);
+          *reinterpret_cast<uint4 *>(ydst + (size_t)l * D + pc * 8) = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (CHAIN && seg + 1 < nseg) {   // publish the state for the next chunk of this sequence (release)
+    float4 *hs = reinterpret_cast<float4 *>(P.chain_state + ((size_t)q * kCh + tid) * kN);
+#pragma unroll
+    for (int j = 0; j < kN / 4; ++j) {
+      float4 v;
+      upk(cs.h[2 * j], v.x, v.y);
+      upk(cs.h[2 * j + 1], v.z, v.w);
+      __stcg(hs + j, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.chain_flag + q), "r"(seg + 1) : "memory");
+  }
+  bulk_wait_read<0>();   // shared memory must outlive the last TMA store's reads
+}
+
+template <typename T>
+void launch_lean(bool pw, bool chain, bool short_ring, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P,
+                 const MaskedMaps &M) {
+#define ACTK_LEAN_LAUNCH(PW, CH, SS) masked_scan_lean_kernel<T, PW, CH, SS><<<grid, kCh, 0, stream>>>(P, M)
+  if (short_ring) {
+    if (chain) { if (pw) ACTK_LEAN_LAUNCH(true, true, 3); else ACTK_LEAN_LAUNCH(false, true, 3); }
+    else { if (pw) ACTK_LEAN_LAUNCH(true, false, 3); else ACTK_LEAN_LAUNCH(false, false, 3); }
+  } else {
+    if (chain) { if (pw) ACTK_LEAN_LAUNCH(true, true, 4); else ACTK_LEAN_LAUNCH(false, true, 4); }
+    else { if (pw) ACTK_LEAN_LAUNCH(true, false, 4); else ACTK_LEAN_LAUNCH(false, false, 4); }
+  }
+#undef ACTK_LEAN_LAUNCH
+}
+
+template void launch_lean<__half>(bool, bool, bool, dim3, cudaStream_t, const MaskedParams<__half> &, const MaskedMaps &);
+template void launch_lean<__nv_bfloat16>(bool, bool, bool, dim3, cudaStream_t, const MaskedParams<__nv_bfloat16> &,
+                                         const MaskedMaps &);
+
+}  // namespace actk

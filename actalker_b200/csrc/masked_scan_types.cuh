@@ -10,6 +10,12 @@ namespace actk {
 constexpr int kCh = 64;  // channels per CTA == threads per CTA
 constexpr int kT = 16;   // time steps per tile
 constexpr int kGroup = 4;  // steps software-pipelined together (ChannelScan::run); see kG in the kernel
+#ifndef ACTK_CHAIN_POLL_NS
+#define ACTK_CHAIN_POLL_NS 200
+#endif
+#ifndef ACTK_LEAN_GROUP
+#define ACTK_LEAN_GROUP 8   // lean kernel, 4-slot ring: steps per software-pipelined group
+#endif
 #ifndef ACTK_STAGES16
 #define ACTK_STAGES16 4
 #endif
@@ -23,6 +29,7 @@ constexpr int ring_stages() { return sizeof(T) == 4 ? 3 : (KS > 0 ? ACTK_STAGES_
 template <typename T>
 struct BranchDev {
   const T *xz, *tail, *xdbl, *xdbl_tail, *delta, *delta_tail, *w_dt;
+  const float *bc32, *bc32_tail;   // lean kernel: fp32 copy of x_dbl's B|C columns, (Bp, n_sel | n_tail, 4N)
   const int *idx;
   const float *A, *Dskip, *dt_bias;
   T *ydir;
@@ -48,6 +55,7 @@ struct MaskedParams {
 };
 struct alignas(64) BranchMaps {
   CUtensorMap xz, xdbl, delta, ydir, xdbl_dt;
+  CUtensorMap bc32, ydir32;   // lean kernel: fp32 B|C boxes (2N wide), per-warp y boxes (32 channels wide)
 };
 struct alignas(64) MaskedMaps {
   BranchMaps m[2];
@@ -57,5 +65,10 @@ struct alignas(64) MaskedMaps {
 // One kernel launch for a given (T, KS); MODE and POWER_A are runtime here.  Defined in masked_scan_kernel.cuh.
 template <typename T, int KS>
 void launch_ks(bool pw, int mode, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P, const MaskedMaps &M);
+
+// Lean kernel (masked_scan_lean.cu): 16-bit I/O, idx == iota, D % 64 == 0, fp32 B|C given; plain or chained launch.
+template <typename T>
+void launch_lean(bool pw, bool chain, bool short_ring, dim3 grid, cudaStream_t stream, const MaskedParams<T> &P,
+                 const MaskedMaps &M);
 
 }  // namespace actk

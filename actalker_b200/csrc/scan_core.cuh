@@ -40,6 +40,10 @@ struct StepIn {
 #define ACTK_FAST_SOFTPLUS16 1   // 16-bit I/O: softplus without the small-argument series (see softplus20_io16)
 #endif
 
+#ifndef ACTK_SOFTPLUS_POLY
+#define ACTK_SOFTPLUS_POLY 0     // 16-bit I/O: log1p on the FMA pipe (softplus20_io16_poly): one MUFU per softplus instead of two
+#endif
+
 // IO16: the activations are 16-bit tensors (selects the softplus form; all arithmetic stays fp32)
 template <bool POWER_A, bool IO16 = false>
 struct ChannelScan {
@@ -64,7 +68,8 @@ struct ChannelScan {
   __device__ __forceinline__ StepIn prologue(float u, float delta_raw) const {
     StepIn s;
     float dt = delta_raw + bias;
-    if (SOFTPLUS) dt = (IO16 && ACTK_FAST_SOFTPLUS16) ? softplus20_io16(dt) : softplus20(dt);
+    if (SOFTPLUS) dt = (IO16 && ACTK_FAST_SOFTPLUS16) ? (ACTK_SOFTPLUS_POLY ? softplus20_io16_poly(dt) : softplus20_io16(dt))
+                                                      : softplus20(dt);
     s.dt = dt;
     s.u = u;
     s.x = dt * u;

@@ -24,13 +24,16 @@ class Problem:
     """C = A @ W^T.  a: (M, K) view with unit column stride; w: (N, K) with unit column stride;
     out: (M, N) view with unit column stride, or (planes, M, N / planes) contiguous planes."""
 
-    __slots__ = ("a", "w", "out", "planes", "silu", "peers", "ldc")
+    __slots__ = ("a", "w", "out", "planes", "silu", "peers", "ldc", "f32")
 
     def __init__(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, planes: int = 1, silu: bool = False,
-                 peers: Sequence[int] = (), ldc: int = 0):
+                 peers: Sequence[int] = (), ldc: int = 0, f32: Optional[torch.Tensor] = None):
         """peers: device addresses of the (M, N) output slot in every rank's gather buffer (fused GEMM + all-gather over
-        NVLink peer memory; `out` is then None and `ldc` the row pitch of those slots, N when 0)."""
+        NVLink peer memory; `out` is then None and `ldc` the row pitch of those slots, N when 0).
+        f32: optional (M, 32 | 64) fp32 tensor that also receives the first columns of the result, widened from the
+        rounded 16-bit values (x_proj's B|C columns for the lean scan kernel)."""
         self.a, self.w, self.out, self.planes, self.silu, self.peers, self.ldc = a, w, out, planes, silu, tuple(peers), ldc
+        self.f32 = f32
 
     def fill(self, p: "_lib.GemmProblem"):
         a, w, out = self.a, self.w, self.out
@@ -61,6 +64,13 @@ class Problem:
         p.plane_stride = plane_stride
         p.M, p.N, p.K, p.planes = M, N, K, self.planes
         p.epilogue = _lib.GEMM_EPI_SILU if self.silu else _lib.GEMM_EPI_NONE
+        if self.f32 is not None:
+            f = self.f32
+            if f.dtype != torch.float32 or f.dim() != 2 or f.shape[0] != M or f.shape[1] not in (32, 64) or f.stride(1) != 1:
+                raise RuntimeError(f"gemm: f32 side output {tuple(f.shape)} {f.dtype} must be ({M}, 32 | 64) float32")
+            p.c_f32, p.ldc_f32, p.f32_cols = f.data_ptr(), (f.stride(0) if M > 1 else f.shape[1]), f.shape[1]
+        else:
+            p.c_f32, p.ldc_f32, p.f32_cols = None, 0, 0
 
 
 def usable(*tensors: Optional[torch.Tensor]) -> bool:

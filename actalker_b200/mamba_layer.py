@@ -136,6 +136,11 @@ _FUSED_KSLABS = (2, 3, 5)   # 16-wide rank slabs the fused dt_proj kernels are b
 # B200 at config 2 the per-tile issue / wait instructions cost the issue-bound scan +0.19 ms (1.51 -> 1.70 ms) while
 # the two cuBLAS dt_proj GEMMs they replace cost 0.14 ms.
 FUSE_DT_PROJ = os.environ.get("ACTK_FUSE_DT", "0") == "1"
+# ACTK_LEAN_SCAN=1: with 16-bit activations under all-ones masks (the shipped pipeline, Inference.py:545-546) the x_proj
+# launch also writes the B|C columns as fp32 and the scan takes the lean kernel (csrc/masked_scan_lean.cu: warp-autonomous
+# tiles, a third less per-tile code).  Bit-identical results; OFF by default: measured on B200 at config 2 it runs in 1.46 ms
+# against 1.43 ms — the 8-step loops, not the code around them, bound the scan (profiles/r02_lean_scan.txt).
+LEAN_SCAN = os.environ.get("ACTK_LEAN_SCAN", "0") == "1"
 
 
 def _rank_pad(R: int):
@@ -369,11 +374,19 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         job = {"i": i, "unit": unit, "w": w, "xw": xw, "fused": fused, "n_sel": n_sel, "n_tail": n_tail, "tail": tail,
                "sel64": sel64 if gather_after else None, "ydir": ydir, "xz_k": xz_k, "src": src}
         if tc:
+            # lean scan kernel: the B|C columns also leave the x_proj launch as fp32 (Bp, n, 4N)
+            lean = LEAN_SCAN and not fused and n_sel == L and Dk % 64 == 0
+            job["bc32"] = torch.empty((Bp, n_sel, 4 * _N), dtype=torch.float32, device=xz.device) if lean else None
             job["xdbl"] = torch.empty((Bp, src.shape[1], xw), dtype=xz.dtype, device=xz.device)
-            xproj.append(gemm.Problem(src.view(-1, D), w_x, job["xdbl"].view(-1, xw)))
+            xproj.append(gemm.Problem(src.view(-1, D), w_x, job["xdbl"].view(-1, xw),
+                                      f32=job["bc32"].view(-1, 4 * _N) if lean else None))
+            job["bc32_tail"] = None
             if n_tail:
                 job["xdbl_tail"] = torch.empty((Bp, n_tail, xw), dtype=xz.dtype, device=xz.device)
-                xproj.append(gemm.Problem(tail.view(-1, D), w_x, job["xdbl_tail"].view(-1, xw)))
+                if lean:
+                    job["bc32_tail"] = torch.empty((Bp, n_tail, 4 * _N), dtype=torch.float32, device=xz.device)
+                xproj.append(gemm.Problem(tail.view(-1, D), w_x, job["xdbl_tail"].view(-1, xw),
+                                          f32=job["bc32_tail"].view(-1, 4 * _N) if lean else None))
             else:
                 job["xdbl_tail"] = None
         else:
@@ -417,6 +430,7 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         b.xz, b.tail, b.xdbl, b.xdbl_tail, b.delta = _ptr(job["xz_k"]), _ptr(tail), _ptr(xdbl), _ptr(xdbl_tail), _ptr(delta)
         b.delta_tail = _ptr(delta_tail)
         b.w_dt = _ptr(w_img) if fused else None
+        b.bc32, b.bc32_tail = _ptr(job.get("bc32")), _ptr(job.get("bc32_tail"))
         b.idx, b.A, b.Dskip, b.dt_bias, b.ydir = _ptr(idxs[i]), _ptr(w["A"]), _ptr(w["Ds"]), _ptr(w["dt_bias"]), _ptr(job["ydir"])
         keep += [xdbl, xdbl_tail, delta, delta_tail, w_img, tail, job]
     if tc:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 10
+#define ACTK_ABI_VERSION 11
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -118,6 +118,12 @@ typedef struct {
   const void *w_dt; /* fused dt_proj (dt_rank_pad != 0): the image actk_pack_dt_proj_weight makes of
                        dt_projs_weight (mamba_layer.py:1443) for THIS D (a channel slice packs its own rows);
                        delta / delta_tail are then unused */
+  const float *bc32, *bc32_tail; /* optional (NULL, NULL): fp32 copies of the B|C columns of xdbl / xdbl_tail,
+                       (Bp, n_sel, 4*N) and (Bp, n_tail, 4*N) contiguous, equal to float(xdbl[..., :4*N]) — what
+                       actk_gemm_problem.c_f32 makes the x_proj launch write.  With them, 16-bit activations, an all-ones
+                       mask (n_sel == L), D % 64 == 0 and delta tensors given, the launch takes the lean kernel
+                       (csrc/masked_scan_lean.cu: warp-autonomous tiles, no per-tile B|C widening); results are
+                       bit-identical either way */
 } actk_branch_args;
 
 typedef struct {
@@ -239,6 +245,13 @@ typedef struct {
    * The caller orders the readers behind all writers (a stream-ordered barrier collective). */
   void *peer_c[ACTK_GEMM_MAX_PEERS];
   int n_peers;
+  /* fp32 side output (planes == 1, n_peers == 0): with f32_cols = 32 or 64 the first f32_cols output columns are ALSO
+   * written to c_f32 (M, f32_cols) fp32, row pitch ldc_f32 elements — the rounded `dtype` result widened, i.e. exactly
+   * float(c[:, :f32_cols]).  x_proj uses it for the B|C columns, which the scan then reads without converting them per
+   * tile (actk_branch_args.bc32). */
+  float *c_f32;
+  long long ldc_f32;
+  int f32_cols;
 } actk_gemm_problem;
 
 int actk_gemm_tn_supported(const actk_gemm_problem *problem, int dtype); /* 1 if the shape / alignment rules hold */
