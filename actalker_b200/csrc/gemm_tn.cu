@@ -505,9 +505,22 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
   // shared memory: ring stages + epilogue staging tiles; three staging tiles unless that leaves fewer than three stages
   const size_t bars = 16 * 6 + 64;
   auto stages_for = [&](int bufs) { return (int)(((size_t)smem_max - 1024 - (size_t)bufs * kEpiBufBytes - bars) / P.stage_bytes); };
+  // Products with several K slabs per tile (in_proj, x_proj, out_proj: K >= 256) gain from a deeper ring — measured on B200,
+  // in_proj with 2 / 3 / 4 / 5 stages: 212 / 168 / 143 / 135 us — so they trade the third staging tile for a fifth stage; the
+  // write-bound dt_proj (one K slab) keeps three staging tiles (149 vs 156 us).  ACTK_GEMM_EPI_BUFS / ACTK_GEMM_STAGES: tuning.
+  int k_slabs_max = 1;
+  for (int g = 0; g < n; ++g) k_slabs_max = P.p[g].k_slabs > k_slabs_max ? P.p[g].k_slabs : k_slabs_max;
   P.epi_bufs = stages_for(3) >= 3 ? 3 : 2;
+  if (k_slabs_max >= 4 && P.n_peers == 0 && stages_for(2) > stages_for(3) && stages_for(3) < 6) P.epi_bufs = 2;
+  if (const char *e = getenv("ACTK_GEMM_EPI_BUFS")) {
+    if (e[0] == '2' || e[0] == '3') P.epi_bufs = e[0] - '0';
+  }
   int stages = stages_for(P.epi_bufs);
   stages = stages > 6 ? 6 : stages;
+  if (const char *e = getenv("ACTK_GEMM_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v < stages) stages = v;
+  }
   if (stages < 2) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: %d bytes of shared memory per block do not hold two pipeline stages", smem_max);
   P.stages = stages;
   const size_t smem = 1024 + (size_t)stages * P.stage_bytes + (size_t)P.epi_bufs * kEpiBufBytes + 16 * (size_t)stages + 64;
