@@ -15,13 +15,13 @@ STATUS_NAMES = {0: "ACTK_OK", 1: "ACTK_ERR_BAD_SHAPE", 2: "ACTK_ERR_BAD_DTYPE", 
                 4: "ACTK_ERR_BAD_ARG", 5: "ACTK_ERR_CUDA", 6: "ACTK_ERR_UNSUPPORTED"}
 ACTK_F32, ACTK_F16, ACTK_BF16 = 0, 1, 2
 ACTK_A_GENERAL, ACTK_A_POWER = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 EXPORTS = ["actk_abi_version", "actk_sm_arch", "actk_last_error", "actk_selective_scan_fwd",
            "actk_masked_scan_fwd", "actk_masked_scan_workspace_bytes", "actk_dt_proj_image_bytes",
            "actk_pack_dt_proj_weight", "actk_merge_ln_outproj_supported", "actk_merge_ln_outproj_fwd", "actk_merge_layernorm_fwd", "actk_gathered_layernorm_fwd", "actk_a_structure",
            "actk_scan_algorithmic_bytes", "actk_peer_buffer_alloc", "actk_peer_buffer_free", "actk_peer_buffer_export",
-           "actk_peer_buffer_open", "actk_peer_buffer_close", "actk_gemm_tn_supported", "actk_gemm_tn_fwd"]
+           "actk_peer_buffer_open", "actk_peer_buffer_close", "actk_gemm_tn_supported", "actk_gemm_tn_fwd", "actk_gather_rows"]
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -129,6 +129,8 @@ def load():
     lib.actk_gemm_tn_supported.restype = _i
     lib.actk_gemm_tn_fwd.argtypes = [C.POINTER(GemmProblem), _i, _i, _vp]
     lib.actk_gemm_tn_fwd.restype = _i
+    lib.actk_gather_rows.argtypes = [_vp, _vp, _vp, _i, _i, _i, _ll, _vp]
+    lib.actk_gather_rows.restype = _i
     lib.actk_scan_algorithmic_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.actk_scan_algorithmic_bytes.restype = _ll
     for name in ("actk_selective_scan_fwd", "actk_masked_scan_fwd",

@@ -173,6 +173,7 @@ static int launch_masked(const actk_masked_scan_args *a, cudaStream_t stream) {
     int j = i + 1;
     while (j < a->n_branches && a->br[j].n_sel > 0 && a->br[j].a_kind == a->br[i].a_kind) ++j;
     P.first_branch = i;
+    P.long_first = (j - i == 2 && a->br[i + 1].n_sel + a->br[i + 1].n_tail > a->br[i].n_sel + a->br[i].n_tail) ? 1 : 0;
     dim3 grid((a->D + kCh - 1) / kCh, a->Bp, 2 * (j - i) * nseg);
     const bool pw = a->br[i].a_kind == ACTK_A_POWER;
     if (chain) {

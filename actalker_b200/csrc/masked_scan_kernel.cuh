@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kCh) masked_scan_kernel(const __grid_constant_
     zi = blockIdx.z / nseg;
   }
   const int d0 = bx * kCh;
-  const int bi = P.first_branch + (zi >> 1);
+  const int bi = P.first_branch + ((zi >> 1) ^ P.long_first);
   const int k = zi & 1;
   const BranchDev<T> br = P.br[bi];
   const BranchMaps &maps = M.m[bi];

@@ -40,6 +40,8 @@ template <typename T>
 struct MaskedParams {
   BranchDev<T> br[2];
   int first_branch;
+  int long_first;   // 1: a two-branch launch hands out the LONGER branch's sequences first (grid z / ticket order), so the short
+                    // branch's CTAs fill the tail instead of opening the launch (partial masks: 513 vs 1551 selected tokens)
   int Bp, L, D, xw;
   int tma_ok;  // D >= 64: boxes are 64 channels wide, a partial last block relies on TMA out-of-bounds handling
   // two-level scan (nseg > 1): the sequence is cut into nseg chunks of whole tiles, scanned by different CTAs

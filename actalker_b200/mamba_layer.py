@@ -320,6 +320,19 @@ def auto_segments(n_ctas: int, min_tiles: int, n_sms: int = 148) -> int:
     return max(1, min(-(-6 * n_sms // n_ctas), min_tiles // 8))
 
 
+def _gather_rows(t: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
+    """t[:, idx, :] for a contiguous (B, rows, row) CUDA tensor and an int32 index list on its device: the own row-gather
+    kernel (16-byte vectors, one warp per row) where rows are multiples of 16 bytes, torch's index_select otherwise."""
+    Bt, rows, width = t.shape
+    if not (t.is_cuda and t.is_contiguous() and (width * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0):
+        return t.index_select(1, idx32.long())
+    out = torch.empty((Bt, idx32.numel(), width), dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device), _timed("gather_rows", t.device):
+        _lib.check(_lib.load().actk_gather_rows(_ptr(t), _ptr(idx32), _ptr(out), Bt, rows, idx32.numel(),
+                                                width * t.element_size(), _stream(t)), "actk_gather_rows")
+    return out
+
+
 def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L: int, idx64s=None, ch_slice=None):
     """Shared launcher: x_proj / dt_proj of every branch + one actk_masked_scan_fwd for all given branches.
     xzs[i]: (Bp, L, D) contiguous; tails[i]: (Bp, n_tail, D) or None; idxs[i]: int32 (n_sel,).
@@ -370,9 +383,9 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         # the narrow x_dbl rows gathered afterwards.
         sel64 = None if n_sel == L else (idx64s[i] if idx64s is not None else idxs[i].long())
         gather_after = sel64 is not None and 2 * n_sel > L
-        src = xz if (sel64 is None or gather_after) else xz.index_select(1, sel64)
+        src = xz if (sel64 is None or gather_after) else _gather_rows(xz, idxs[i])
         job = {"i": i, "unit": unit, "w": w, "xw": xw, "fused": fused, "n_sel": n_sel, "n_tail": n_tail, "tail": tail,
-               "sel64": sel64 if gather_after else None, "ydir": ydir, "xz_k": xz_k, "src": src}
+               "sel64": sel64 if gather_after else None, "idx32": idxs[i], "ydir": ydir, "xz_k": xz_k, "src": src}
         if tc:
             # lean scan kernel: the B|C columns also leave the x_proj launch as fp32 (Bp, n, 4N)
             lean = LEAN_SCAN and not fused and n_sel == L and Dk % 64 == 0
@@ -401,7 +414,7 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
         i, w, xw, n_sel, n_tail, tail = job["i"], job["w"], job["xw"], job["n_sel"], job["n_tail"], job["tail"]
         xdbl, xdbl_tail, fused = job["xdbl"], job["xdbl_tail"], job["fused"]
         if job["sel64"] is not None:
-            xdbl = xdbl.index_select(1, job["sel64"])                          # (Bp, n_sel, xw), sequence order
+            xdbl = _gather_rows(xdbl, job["idx32"])                            # (Bp, n_sel, xw), sequence order
         if sliced and tail is not None:
             tail = tail[..., lo:hi].contiguous()
         delta = delta_tail = w_img = None

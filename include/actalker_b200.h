@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ACTK_ABI_VERSION 11
+#define ACTK_ABI_VERSION 12
 #define ACTK_DSTATE 16 /* d_state of every live layer (TransformerSTmodel.py:3962-3971) */
 
 typedef enum {
@@ -263,6 +263,12 @@ int actk_gemm_tn_fwd(const actk_gemm_problem *problems, int n_problems, int dtyp
  *     (the Python layer caches the answer per parameter version).
  * ------------------------------------------------------------------------------------------- */
 int actk_a_structure(const float *A, int dim, int dstate, float rel_tol, int *flag_dev, void *stream);
+
+/* Row gather of the partial-mask path (mamba_layer.py:1963, 1974: xz[:, idx, :]): dst (batch, n_idx, row) =
+ * src (batch, rows_src, row)[:, idx, :] with rows of row_bytes (a multiple of 16; pointers 16-byte aligned), idx (n_idx)
+ * int32 device, values in [0, rows_src). */
+int actk_gather_rows(const void *src, const int *idx, void *dst, int batch, int rows_src, int n_idx, long long row_bytes,
+                     void *stream);
 
 /* Gather buffers for the fused push all-gather of (3) (peer_out[]): cudaMalloc'ed on the current device, exported
  * as a 64-byte CUDA IPC handle, opened by the other ranks' processes (mapped with peer access into the opener's
