@@ -151,7 +151,9 @@ __device__ __forceinline__ int gemm_problem_of(const GemmParams &P, int t) {
 // MH: row halves per tile.  1 (default): 128-row tiles, two accumulator buffers.  2 (ACTK_GEMM_MH=2): 256-row tiles —
 // every W slab feeds two M = 128 MMAs, which cuts the TMA fill traffic per multiply-add by a third (see launch_gemm for
 // what that measured).
-template <typename T, int EPI, int MH>
+// F32SIDE: some problem of the launch has the fp32 side output (compile-time, like EPI: the write-bound dt_proj launch lost
+// 20 us to the mere presence of the extra chunk loop in its epilogue).
+template <typename T, int EPI, int MH, bool F32SIDE>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t gemm_smem[];
   const uint32_t base = (smem_u32(gemm_smem) + 1023u) & ~1023u;     // SWIZZLE_128B atoms want 1024-byte alignment
@@ -251,10 +253,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       // fp32 side output (x_proj: the scan reads B|C as fp32 without widening them per tile): the leading f32_cols
       // columns of the first column tile go out a second time, as the ROUNDED result widened to fp32, in extra chunks of
       // 32 fp32 columns (128-byte staging rows, the same swizzle and the same staging-tile rotation as the 16-bit chunks)
-      const int nf32 = (MH == 1 && n == 0) ? (pr.f32_cols >> 5) : 0;
+      const int nf32 = (F32SIDE && MH == 1 && n == 0) ? (pr.f32_cols >> 5) : 0;
       for (int hc = 0; hc < MH * nchunks + nf32; ++hc, ++chunk_count) {
         const uint32_t buf = epi_base + (chunk_count % (uint32_t)P.epi_bufs) * kEpiBufBytes;
-        if (hc >= MH * nchunks) {
+        if (F32SIDE && hc >= MH * nchunks) {
           const int v = hc - MH * nchunks;      // fp32 columns [32 v, 32 v + 32): every warp converts 16 of them for its rows
           const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256;
           uint32_t f16r[16];
@@ -524,9 +526,12 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
   if (stages < 2) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: %d bytes of shared memory per block do not hold two pipeline stages", smem_max);
   P.stages = stages;
   const size_t smem = 1024 + (size_t)stages * P.stage_bytes + (size_t)P.epi_bufs * kEpiBufBytes + 16 * (size_t)stages + 64;
-  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH>;
-  static int configured[64][2] = {};   // per device and epilogue: dynamic shared memory limit raised
-  const int ei = epilogue == ACTK_GEMM_EPI_SILU ? 1 : 0;
+  bool f32side = false;
+  for (int g = 0; g < n; ++g) f32side = f32side || P.p[g].f32_cols != 0;
+  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, false> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, false>;
+  if (f32side) kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, true> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, true>;
+  static int configured[64][4] = {};   // per device and kernel variant: dynamic shared memory limit raised
+  const int ei = (epilogue == ACTK_GEMM_EPI_SILU ? 1 : 0) + (f32side ? 2 : 0);
   if (dev < 64 && !configured[dev][ei]) {
     ACTK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     configured[dev][ei] = 1;
