@@ -532,7 +532,13 @@ def run_ours(args, rank, world, local_rank):
                          # the roofline fraction this kernel would show if it ran exactly at that floor: what
                          # fp32 per-(channel, state) exponentials allow on 148 SMs, whatever the memory system does
                          "frac_at_floor": (q / peak / 1e6) / floor_ms,
-                         "source": fc["source"]}},
+                         "source": fc["source"]},
+                     # the same step's instruction mix run in isolation (no tiles, no HBM traffic) at saturating occupancy,
+                     # next to the rate the kernel sustains over the whole launch (tile plumbing, chained chunks included)
+                     "step_mix": {
+                         "saturated_smsp_cycles_per_warp_step": fc["scan_hot_loop"][kind]["step_mix_saturated_cycles_per_warp_step"],
+                         "kernel_smsp_cycles_per_warp_step": scan_ms * 1e-3 * fc["sm_clock_mhz"] * 1e6 * 148 * 4 / (updates / 16 / 32),
+                         "what": fc["scan_hot_loop"][kind]["step_mix_what"]}},
         "e2e": {"value": tokens / (ms_e2e * 1e-3) / 1e9, "unit": "Gtokens/s",
                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (hx, hid, hcd)),
                 "d2h_bytes_per_step": hy.numel() * hy.element_size(), "ms_per_step": ms_e2e,
