@@ -49,6 +49,97 @@ __device__ __forceinline__ void unpack8(const Raw8<T> &r, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = IO<T>::ld(e + i);
   }
 }
+// Packed 16-bit add / multiply with ONE rounding to nearest-even per element (add.rn.bf16x2 / .f16x2, SASS HADD2 / HMUL2):
+// exactly what the reference's `a + b` / `a * w` on two 16-bit tensors produce (the fp32 sum or product of two 8- or
+// 11-bit significands is exact, then rounded once) — at a quarter of the instructions of widen, add, round, re-widen.
+template <typename T> __device__ __forceinline__ uint32_t add2_16(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add2_16<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t add2_16<__half>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t add2_16<float>(uint32_t a, uint32_t) { return a; }   // never used
+template <typename T> __device__ __forceinline__ uint32_t mul2_16(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t mul2_16<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t mul2_16<__half>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t mul2_16<float>(uint32_t a, uint32_t) { return a; }   // never used
+template <typename T>
+__device__ __forceinline__ uint4 add8_16(uint4 a, uint4 b) {
+  return make_uint4(add2_16<T>(a.x, b.x), add2_16<T>(a.y, b.y), add2_16<T>(a.z, b.z), add2_16<T>(a.w, b.w));
+}
+template <typename T>
+__device__ __forceinline__ uint4 mul8_16(uint4 a, uint32_t w2) {
+  return make_uint4(mul2_16<T>(a.x, w2), mul2_16<T>(a.y, w2), mul2_16<T>(a.z, w2), mul2_16<T>(a.w, w2));
+}
+
+// One vector of a row through the merge: per branch the direction sum (selected rows) or the in_proj value, the optional
+// row weight, then the branch sum — every step rounded where the reference holds a `dtype` tensor.
+template <typename T>
+__device__ __forceinline__ void merge_vec(const Raw8<T> (&raw)[2][2], const bool (&sel)[2], const actk_merge_ln_args &a, int l,
+                                          float (&acc)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      if (br >= a.n_branches) break;
+      uint4 t = raw[br][0].w[0];
+      if (sel[br]) {
+        t = add8_16<T>(t, raw[br][1].w[0]);
+        if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
+          const uint32_t w = *reinterpret_cast<const uint16_t *>((const T *)a.row_weight[br] + l);
+          t = mul8_16<T>(t, w | (w << 16));
+        }
+      }
+      m = br == 0 ? t : add8_16<T>(t, m);
+    }
+    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if constexpr (IO<T>::is_bf16) {
+        acc[2 * j] = __uint_as_float(mw[j] << 16);
+        acc[2 * j + 1] = __uint_as_float(mw[j] & 0xffff0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&mw[j]));
+        acc[2 * j] = f.x;
+        acc[2 * j + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      if (br >= a.n_branches) break;
+      float t[8];
+      unpack8<T>(raw[br][0], t);
+      if (sel[br]) {
+        float g[8];
+        unpack8<T>(raw[br][1], g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] + g[e]);
+        if (a.row_weight[br]) {
+          const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
+    }
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void store8(T *p, const float (&v)[8]) {
   if (sizeof(T) == 4) {
@@ -109,25 +200,7 @@ __global__ void __launch_bounds__(128, (VPL <= 4 && sizeof(T) == 2) ? ACTK_MERGE
       const int i = i0 + ii, v = lane + 32 * i;
       if (v < nvec) {
         float acc[8];
-#pragma unroll
-        for (int br = 0; br < 2; ++br) {
-          if (br >= a.n_branches) break;
-          float t[8];
-          unpack8<T>(raw[ii][br][0], t);
-          if (sel[br]) {
-            float g[8];
-            unpack8<T>(raw[ii][br][1], g);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] + g[e]);
-            if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
-              const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
-        }
+        merge_vec<T>(raw[ii], sel, a, l, acc);
 #pragma unroll
         for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
       }
@@ -228,25 +301,7 @@ __global__ void __launch_bounds__(128, (VPL <= 4 && sizeof(T) == 2) ? ACTK_MERGE
       const int i = i0 + ii, v = lane + 32 * (part + WPR * i);
       if (v < nvec) {
         float acc[8];
-#pragma unroll
-        for (int br = 0; br < 2; ++br) {
-          if (br >= a.n_branches) break;
-          float t[8];
-          unpack8<T>(raw[ii][br][0], t);
-          if (sel[br]) {
-            float g[8];
-            unpack8<T>(raw[ii][br][1], g);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] + g[e]);
-            if (a.row_weight[br]) {   // multiplicative region blend of SS2D_cond_v8 / v9 (mamba_layer.py:1777-1797)
-              const float w = IO<T>::ld((const T *)a.row_weight[br] + l);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t[e] = IO<T>::rnd(t[e] * w);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = br == 0 ? t[e] : IO<T>::rnd(t[e] + acc[e]);
-        }
+        merge_vec<T>(raw[ii], sel, a, l, acc);
 #pragma unroll
         for (int e = 0; e < 8; ++e) { x[i][e] = acc[e]; sum += acc[e]; }
       }
