@@ -417,7 +417,9 @@ def run_ours(args, rank, world, local_rank):
         # ---------------- device-resident timed region (value, roofline)
         sampler = ClockSampler(local_rank)
         sampler.start()
-        ml.TIMING = {}
+        # inside the timed region only the roofline's kernel is bracketed by CUDA events (on its launching stream): a pair
+        # of event records costs the stream ~5 us, and bracketing all seven launches made the step 3 % slower than it is
+        ml.TIMING = {"only": {"masked_scan"}}
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         start.record()
@@ -427,10 +429,20 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         sampler.stop_flag = True
         ms_total = start.elapsed_time(end)
-        events, ml.TIMING = ml.TIMING.get("events", []), None
+        n_launches = ml.TIMING.get("launches", 0)
+        events = ml.TIMING.get("events", [])
         kern = {}
         for name, s, e in events:
             kern.setdefault(name, []).append(s.elapsed_time(e))
+        # the split of the step over ALL its launches: a second, separately instrumented pass of the same K steps
+        ml.TIMING = {}
+        for i in range(args.steps):
+            layer(*dsets[i % nrot], masks)
+        torch.cuda.synchronize(dev)
+        split_events, ml.TIMING = ml.TIMING.get("events", []), None
+        kern_all = {}
+        for name, s, e in split_events:
+            kern_all.setdefault(name, []).append(s.elapsed_time(e))
         # ---------------- end-to-end through the public host-buffer API: every step uploads its inputs from pinned
         # host memory and downloads its result; HostStreamedLayer overlaps step i+1's H2D and step i-1's D2H with
         # step i's compute (three streams, double-buffered staging) — all bytes still move inside the timed region
@@ -474,9 +486,9 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = peaks()
     q = scan_bytes(Bp, L, D // world if channel else D, es)   # per-rank launch
     scan_ms = statistics.mean(kern["masked_scan"])
-    merge_ms = statistics.mean(kern["merge_ln"])
-    per_step = {k: sum(v) / args.steps for k, v in kern.items()}            # ms per step, summed over the step's launches
-    launches_per_step = len(events) / args.steps
+    merge_ms = statistics.mean(kern_all["merge_ln"])
+    per_step = {k: sum(v) / args.steps for k, v in kern_all.items()}        # ms per step, summed over the step's launches
+    launches_per_step = n_launches / args.steps
     achieved = q / (scan_ms * 1e-3) / 1e9
     updates = Bp * (2 * L + 35) * 2 * D * 16
     traffic = None
