@@ -12,7 +12,12 @@ ACTK_TC_GEMM=0 python bench.py --no-cpu-baseline > "$O/bench_cublas_route.json" 
 ACTK_FUSE_DT=1 python bench.py --no-cpu-baseline > "$O/bench_fused_dt.json" 2>/dev/null; echo "fused_dt_rc=$?"
 ACTK_FUSE_LN_OUT=1 python bench.py --no-cpu-baseline > "$O/bench_fused_lnout.json" 2>/dev/null; echo "fused_ln_rc=$?"
 python bench.py --dtype f16 --no-cpu-baseline > "$O/bench_f16.json" 2>/dev/null; echo "f16_rc=$?"
+ACTK_LEAN_SCAN=1 python bench.py --no-cpu-baseline > "$O/bench_lean_scan.json" 2>/dev/null; echo "lean_rc=$?"
+if [ -n "$REFERENCE_ARM" ]; then   # ~21 s of CPU per step on the 16-core box: only when asked for
 python bench.py --impl reference --steps 3 --warmup 1 > "$O/bench_reference.json" 2>/dev/null; echo "reference_rc=$?"
+fi
+python tools/bench_gemm_tn.py > "$O/gemm_tn_vs_cublas.jsonl" 2>/dev/null; echo "gemm_rc=$?"
+python tools/profile_gaps.py > "$O/timeline.txt" 2>/dev/null
 python tools/bench_configs.py > "$O/configs_3_5.jsonl" 2>/dev/null; echo "configs_rc=$?"
 python tools/bench_operator.py > "$O/operator.txt" 2>/dev/null; echo "operator_rc=$?"
 python tools/bench_latency.py > "$O/latency_graph.jsonl" 2>/dev/null

@@ -10,6 +10,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launches_rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:masked_scan -s 4 -c 1 -o "$O/masked_scan_general" $B > /dev/null 2>&1
 echo "scan_rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:merge_ln -s 4 -c 1 -o "$O/merge_ln" $B > /dev/null 2>&1
+echo "merge_rc=$?"
 i=16
 for name in inproj xproj dtproj outproj; do
   ncu --set full --clock-control none --import-source on -k regex:gemm_tn -s $i -c 1 -o "$O/gemm_tn_$name" $B > /dev/null 2>&1
