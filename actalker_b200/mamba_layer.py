@@ -299,6 +299,8 @@ class SS2D_Unit(nn.Module):
 
 
 SCAN_SEGMENTS = None   # None: choose per call (auto_segments); an int forces that many chunks (tests, tuning)
+SCAN_BATCH_HINT = None # an int: choose the two-level launch shape as a call of that many frames would (a batch-split call that
+                       # must reproduce the unsplit call bit for bit: the two-level scan re-associates fp32 sums)
 SCAN_CHAIN = None      # None: choose per call (auto_chain); an int forces that many chained chunks (0/1 = off)
 POISON_OUTPUTS = False # tests: pre-fill the scan output with NaN so a row the kernel fails to write cannot go unnoticed
 
@@ -460,7 +462,8 @@ def _scan_branches(units: List[SS2D_Unit], xzs, tails, idxs, n_sels, Bp: int, L:
     if live:
         min_tiles = min(-(-(n_sels[i] + (0 if tails[i] is None else tails[i].shape[1])) // 16) for i in live)
         n_ctas = -(-Dk // 64) * Bp * 2 * len(live)
-        args.nseg = SCAN_SEGMENTS if SCAN_SEGMENTS is not None else auto_segments(n_ctas, min_tiles)
+        n_ctas_shape = n_ctas if SCAN_BATCH_HINT is None else -(-Dk // 64) * SCAN_BATCH_HINT * 2 * len(live)
+        args.nseg = SCAN_SEGMENTS if SCAN_SEGMENTS is not None else auto_segments(n_ctas_shape, min_tiles)
         if args.nseg <= 1:
             args.chain_chunks = SCAN_CHAIN if SCAN_CHAIN is not None else auto_chain(n_ctas, min_tiles)
         ws_bytes = lib.actk_masked_scan_workspace_bytes(ct.byref(args))

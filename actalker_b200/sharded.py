@@ -85,7 +85,10 @@ class BatchShardedCall:
 
     Partition: equal blocks of ceil(B'/P) frames, the last blocks shorter or empty.  The gather buffer has P * ceil(B'/P)
     frame slots and the result is its first B' frames, so the NCCL all-gather (equal contributions) writes the output in
-    place: no padding copy, no re-layout.  Frames are independent, so the result is bit-identical to the one-GPU call.
+    place: no padding copy, no re-layout.  Frames are independent, so the result equals the one-GPU call bit for bit as long
+    as both take the same scan launch shape; a rank left with fewer than ~5 frames (B' = 25 over 4 or 8 GPUs) would take the
+    two-level scan, which re-associates fp32 sums (differences of one 16-bit rounding step): `exact=True` pins the unsplit
+    call's launch shape instead (a 4-frame block then scans in 0.84 instead of 0.75 ms).
     tiles > 1: a rank's block is cut into that many pieces; the gather of piece i runs on a side stream under the compute
     of piece i+1 (the pieces' slots are strided in the output, so each piece gathers into its own buffer and one copy per
     piece, also on the side stream, places it)."""
@@ -93,7 +96,7 @@ class BatchShardedCall:
     MIN_FRAMES_PER_TILE = 25   # below ~1000 scan CTAs per launch the scan is latency-bound: cutting further costs more than
                                # the overlapped gather saves (B200, N=2, B'=25: 13 frames in two pieces 1.75 ms, in one 1.2 ms)
 
-    def __init__(self, layer: SS2D_cond_v10, group=None, tiles: int = 1, gather: str = "nccl"):
+    def __init__(self, layer: SS2D_cond_v10, group=None, tiles: int = 1, gather: str = "nccl", exact: bool = False):
         """gather="nccl": NCCL all-gather of the blocks (in place in the padded output).
         gather="p2p": fused compute + collective — the out_proj kernel's epilogue stores every output tile straight into
         all ranks' gather buffers over NVLink peer memory (one TMA store per rank and tile; CUDA IPC buffers of
@@ -103,6 +106,7 @@ class BatchShardedCall:
             raise ValueError("gather must be 'nccl' or 'p2p'")
         self.layer, self.group, self.max_tiles, self.gather = layer, group, max(1, int(tiles)), gather
         self.tiles = self.max_tiles
+        self.exact = bool(exact)
         self._peer = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -121,6 +125,16 @@ class BatchShardedCall:
         return {"compute": s.elapsed_time(c), "gather_tail": c.elapsed_time(e)}
 
     def __call__(self, x, id_emb, conds, masks):
+        if self.exact and self.world > 1:
+            from . import mamba_layer as ml
+            prev, ml.SCAN_BATCH_HINT = ml.SCAN_BATCH_HINT, x.shape[0]
+            try:
+                return self._call(x, id_emb, conds, masks)
+            finally:
+                ml.SCAN_BATCH_HINT = prev
+        return self._call(x, id_emb, conds, masks)
+
+    def _call(self, x, id_emb, conds, masks):
         layer, P, rank = self.layer, self.world, self.rank
         Bp, L, dm = x.shape
         if P == 1:

@@ -351,13 +351,16 @@ def strong_scaling(args, layer, dev, rank, world, dtype, barrier, steps):
             same = bool(torch.equal(res["t1_y"], res["tN_y"]))
             diff = (res["t1_y"].float() - res["tN_y"].float()).abs().max()
             same_push = bool(torch.equal(res["tN_y"], res["tP_y"])) if push else True   # same kernels, other transport
-        flag = torch.tensor([1 if same else 0, 1 if same_push else 0], device=dev)
+            # exact=True pins the unsplit call's scan launch shape on every rank: bit-identical whatever the split
+            same_exact = bool(torch.equal(res["t1_y"], BatchShardedCall(layer, exact=True)(x, idm, cd, masks)))
+        flag = torch.tensor([1 if same else 0, 1 if same_push else 0, 1 if same_exact else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
         out[f"Bp{Bp}"] = {"ms_1gpu": res["t1"], "ms_Ngpu": res["tN"], "efficiency": res["t1"] / (world * res["tN"]),
                           "frames_per_rank": [hi - lo for lo, hi in call.plan(Bp).all_bounds()],
                           "gather_bytes_per_rank": Bp * L * d_model * x.element_size(),
                           "bit_identical_to_one_gpu": bool(flag[0].item()), "max_abs_diff_vs_one_gpu": diff.item(),
+                          "bit_identical_to_one_gpu_with_exact_launch_shape": bool(flag[2].item()),
                           "phases_ms": call.phase_ms(),
                           "tiles_per_rank": call.tiles}
         if push:   # fused out_proj + all-gather over NVLink peer memory (TMA stores into every rank's buffer)
