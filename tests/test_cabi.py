@@ -237,3 +237,51 @@ def test_mask_index_lands_on_the_layers_device_and_weights_are_cached():
     with torch.no_grad():
         u.Ds.add_(1.0)                                       # a parameter changed in place: everything is rebuilt
     assert u.weights_for(torch.bfloat16) is not w
+
+
+def test_ctypes_structures_have_the_headers_layout(tmp_path):
+    """Every argument structure of include/actalker_b200.h compiled by a plain C compiler (the header is C: no CUDA, no
+    torch types) has the size and the field offsets of its ctypes mirror in actalker_b200/_lib.py."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"actk_scan_args": _lib.ScanArgs, "actk_branch_args": _lib.BranchArgs,
+               "actk_masked_scan_args": _lib.MaskedScanArgs, "actk_merge_ln_args": _lib.MergeLnArgs,
+               "actk_gemm_problem": _lib.GemmProblem}
+    header = os.path.join(ROOT, "include", "actalker_b200.h")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{header}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([cc, "-std=c99", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_gather_rows_and_fp32_side_output_validation():
+    """actk_gather_rows and the fp32 side output of actk_gemm_tn_fwd reject bad arguments before any launch."""
+    lib = _lib.load()
+    assert lib.actk_gather_rows(None, None, None, 1, 1, 1, 16, None) == _status("ACTK_ERR_BAD_ARG")
+    assert lib.actk_gather_rows(1 << 20, 1 << 21, 1 << 22, 1, 8, 4, 24, None) == _status("ACTK_ERR_BAD_ALIGN")
+    assert lib.actk_gather_rows(1 << 20, 1 << 21, 1 << 22, 0, 8, 4, 16, None) == _status("ACTK_ERR_BAD_SHAPE")
+    assert lib.actk_gather_rows(1 << 20, 1 << 21, 1 << 22, 2, 8, 0, 16, None) == _lib.ACTK_OK      # nothing selected: no launch
+    arr = (_lib.GemmProblem * 1)()
+    p = arr[0]
+    p.a, p.w, p.c = 1 << 20, 1 << 21, 1 << 22
+    p.M, p.N, p.K, p.planes, p.lda, p.ldw, p.ldc = 128, 128, 64, 1, 64, 64, 128
+    p.f32_cols = 64                                   # no destination
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_ARG")
+    p.c_f32, p.ldc_f32, p.f32_cols = 1 << 23, 64, 48  # 32 or 64 columns only
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) == _status("ACTK_ERR_BAD_SHAPE")
+    p.f32_cols, p.ldc_f32 = 64, 32                    # pitch smaller than the columns
+    assert lib.actk_gemm_tn_fwd(arr, 1, _lib.ACTK_BF16, None) in (_status("ACTK_ERR_BAD_SHAPE"), _status("ACTK_ERR_BAD_ALIGN"))
