@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(kCh) masked_scan_lean_kernel(const __grid_cons
   // sequence position (== latent row) held by shared-memory row 0 of tile t
   auto first_row = [&](int t) { return k == 0 ? t * kT : Lp - kT - t * kT; };
 
-  // Tile t -> its ring slot.  Fast: the elected lane waits for the slot's release, arms the barrier with the byte count
-  // and issues three tensor-map loads.  Ragged: the whole warp gathers 16-byte pieces (u, delta, fp32 B|C rows of the
+  // Tile t -> its ring slot.  Fast: the warp waits for the slot's release (same outcome in every lane), one lane arms the
+  // barrier with the byte count and issues three tensor-map loads (predicated inside the asm).  Ragged: the whole warp gathers 16-byte pieces (u, delta, fp32 B|C rows of the
   // valid positions) with cp.async tracked by the same barrier, then one plain arrival.
   auto issue_tile = [&](int t) {
     const int tr = t - t_begin, sn = tr % S, use = tr / S;
