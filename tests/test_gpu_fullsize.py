@@ -116,6 +116,27 @@ def test_batch_permutation_is_exact_and_calls_are_deterministic():
     assert torch.equal(yp, y1[perm])
 
 
+def test_a_block_of_frames_reproduces_the_whole_call_when_the_launch_shape_is_pinned():
+    """Frames are independent (mamba_layer.py:1955-1986 has no cross-frame operation), so a block of a call's frames must
+    give the call's own rows.  Four frames alone would take the two-level scan (fp32 sums associate differently: one 16-bit
+    rounding step of difference is allowed); with SCAN_BATCH_HINT = the whole call's frame count — what
+    BatchShardedCall(exact=True) sets on every rank — the block is bit-identical."""
+    from actalker_b200 import mamba_layer as ml
+    layer = make_layer(torch.bfloat16)
+    x, idm, cd = inputs(torch.bfloat16)
+    m = masks("ones", torch.bfloat16)
+    with torch.no_grad():
+        whole = layer(x, idm, cd, m)
+        free = layer(x[3:7], idm[3:7], cd[3:7], m)
+        try:
+            ml.SCAN_BATCH_HINT = B
+            pinned = layer(x[3:7], idm[3:7], cd[3:7], m)
+        finally:
+            ml.SCAN_BATCH_HINT = None
+    assert torch.equal(pinned, whole[3:7])
+    assert torch.allclose(free.float(), whole[3:7].float(), rtol=3e-2, atol=3e-2)
+
+
 def test_unit_direction_symmetry_full_size():
     """Swapping the two directions' weights and reversing the token order reverses the output
     (mamba_layer.py:1518-1547)."""
