@@ -46,7 +46,6 @@ struct GemmProblemDev {
   CUtensorMap c32;       // 32-column store boxes (SWIZZLE_64B) for the last chunk of a tile whose width is 32 mod 64
   CUtensorMap cf32;      // fp32 side output: boxes of 32 fp32 columns x 128 rows (SWIZZLE_128B)
   int f32_cols;          // leading output columns that are ALSO written, widened from the rounded result, to c_f32 (0 / 32 / 64)
-  int tiles_per_plane;
   int n_tiles;        // column tiles per row tile
   int k_slabs;
   int bn;             // columns per tile (multiple of 32, <= 256)
@@ -114,6 +113,44 @@ __device__ __forceinline__ void gemm_umma(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void gemm_commit(uint32_t bar) {   // arrives once every MMA issued so far by this thread is done
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster work on one 256-row tile.  Each loads its own 128 rows of A and
+// HALF of the W slab; the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write both
+// CTAs' tensor memory, so a W byte is fetched from L2 once per 256 output rows.
+__device__ __forceinline__ uint32_t gemm_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t gemm_leader_addr(uint32_t smem_addr) {   // the same offset in the leader CTA's shared memory
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
+  return r;
+}
+__device__ __forceinline__ void gemm_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// load into THIS CTA's shared memory, bytes counted on the LEADER's mbarrier (bar: a shared::cluster address)
+__device__ __forceinline__ void gemm_tma_load_2d_pair(uint32_t dst_smem, const void *tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void gemm_umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void gemm_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void gemm_bar_arrive_cluster(uint32_t bar) {   // bar: a shared::cluster address (gemm_leader_addr)
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void gemm_tmem_ld16(uint32_t taddr, uint32_t *r) {   // no wait: see gemm_tmem_wait32
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -153,7 +190,8 @@ __device__ __forceinline__ int gemm_problem_of(const GemmParams &P, int t) {
 // what that measured).
 // F32SIDE: some problem of the launch has the fp32 side output (compile-time, like EPI: the write-bound dt_proj launch lost
 // 20 us to the mere presence of the extra chunk loop in its epilogue).
-template <typename T, int EPI, int MH, bool F32SIDE>
+// PAIR: two CTAs per 256-row tile (cta_group::2, above); launched as clusters of two, MH == 1.
+template <typename T, int EPI, int MH, bool F32SIDE, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t gemm_smem[];
   const uint32_t base = (smem_u32(gemm_smem) + 1023u) & ~1023u;     // SWIZZLE_128B atoms want 1024-byte alignment
@@ -165,10 +203,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
                  tempty_bar = tfull_bar + 16;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gemm_smem + (tempty_bar + 16 - smem_u32(gemm_smem)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? gemm_cluster_rank() : 0;                   // 0: the CTA that issues the pair's MMAs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { gemm_bar_init(full_bar + 8 * s, 1); gemm_bar_init(empty_bar + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { gemm_bar_init(tfull_bar + 8 * b, 1); gemm_bar_init(tempty_bar + 8 * b, kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { gemm_bar_init(tfull_bar + 8 * b, 1); gemm_bar_init(tempty_bar + 8 * b, PAIR ? 2 * kEpiWarps : kEpiWarps); }
     mbar_fence_init();
     for (int g = 0; g < P.n_problems; ++g) {
       tmap_prefetch(&P.p[g].a); tmap_prefetch(&P.p[g].w); tmap_prefetch(&P.p[g].c); tmap_prefetch(&P.p[g].c32);
@@ -177,41 +216,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     for (int pe = 0; pe < P.n_peers; ++pe) tmap_prefetch(&P.peer_c[pe]);
   }
   __syncwarp();
-  if (warp == 1) {   // 2 accumulator buffers x 256 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // 2 accumulator buffers x 256 columns (PAIR: warp 1 of both CTAs, the same columns in both)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) gemm_cluster_sync(); else __syncthreads();   // PAIR: the peer's barriers are initialised before anyone signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {   // ---------------------------------------------------------------- TMA producer
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = (PAIR ? blockIdx.x >> 1 : blockIdx.x); tile < P.total_tiles; tile += (PAIR ? gridDim.x >> 1 : gridDim.x)) {
         const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
         const int local = tile - pr.tile_begin;
         const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
-        const uint32_t tx = kATile + (uint32_t)pr.bn * (kBK * 2);
+        const uint32_t tx = kATile + (PAIR ? (uint32_t)pr.bn >> 1 : (uint32_t)pr.bn) * (kBK * 2);   // PAIR: half of the W slab
         for (int ks = 0; ks < pr.k_slabs; ++ks, ++it) {
           const uint32_t s = it % S, use = it / S;
           if (use > 0) gemm_bar_wait(empty_bar + 8 * s, (use - 1) & 1);
           const uint32_t sa = base + s * P.stage_bytes;
-          gemm_bar_expect_tx(full_bar + 8 * s, tx);
-          gemm_tma_load_2d(sa, &pr.a, ks * kBK, m * (MH * kBM), full_bar + 8 * s);       // box of MH * 128 rows
-          gemm_tma_load_2d(sa + kATile, &pr.w, ks * kBK, n * pr.bn, full_bar + 8 * s);
+          if (PAIR) {    // both CTAs' bytes are counted on the leader's barrier, which its own producer arms for both
+            if (rank == 0) gemm_bar_expect_tx(full_bar + 8 * s, 2 * tx);
+            const uint32_t lb = gemm_leader_addr(full_bar + 8 * s);
+            gemm_tma_load_2d_pair(sa, &pr.a, ks * kBK, (2 * m + (int)rank) * kBM, lb);
+            gemm_tma_load_2d_pair(sa + kATile, &pr.w, ks * kBK, n * pr.bn + (int)rank * (pr.bn >> 1), lb);
+          } else {
+            gemm_bar_expect_tx(full_bar + 8 * s, tx);
+            gemm_tma_load_2d(sa, &pr.a, ks * kBK, m * (MH * kBM), full_bar + 8 * s);       // box of MH * 128 rows
+            gemm_tma_load_2d(sa + kATile, &pr.w, ks * kBK, n * pr.bn, full_bar + 8 * s);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {   // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0 && rank == 0) {   // ------------------------------------------------------- MMA issuer
       uint32_t it = 0, tc = 0;
       constexpr uint32_t fmt = IO<T>::is_bf16 ? 1u : 0u;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+      for (int tile = (PAIR ? blockIdx.x >> 1 : blockIdx.x); tile < P.total_tiles; tile += (PAIR ? gridDim.x >> 1 : gridDim.x), ++tc) {
         const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(pr.bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(pr.bn >> 3) << 17) | ((uint32_t)((PAIR ? 2 * kBM : kBM) >> 4) << 24);
         const uint32_t b = P.acc_bufs == 2 ? (tc & 1) : 0, ub = P.acc_bufs == 2 ? (tc >> 1) : tc;
         if (ub > 0) gemm_bar_wait(tempty_bar + 8 * b, (ub - 1) & 1);   // the epilogue has read this buffer's previous tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -224,12 +275,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
 #pragma unroll
-            for (int hh = 0; hh < MH; ++hh)
-              gemm_umma(acc + hh * P.acc_hstride, gemm_sw128_desc(sa + hh * kABytes + k * 32), gemm_sw128_desc(sw + k * 32), idesc,
-                        (uint32_t)((ks | k) != 0));
-          gemm_commit(empty_bar + 8 * s);    // the slab may be overwritten once these MMAs have read it
+            for (int hh = 0; hh < MH; ++hh) {
+              // PAIR, M = 256: rows 0-127 from this CTA's A slab, 128-255 from the peer's; the W halves likewise
+              if (PAIR) gemm_umma_pair(acc, gemm_sw128_desc(sa + k * 32), gemm_sw128_desc(sw + k * 32), idesc, (uint32_t)((ks | k) != 0));
+              else gemm_umma(acc + hh * P.acc_hstride, gemm_sw128_desc(sa + hh * kABytes + k * 32), gemm_sw128_desc(sw + k * 32), idesc,
+                             (uint32_t)((ks | k) != 0));
+            }
+          // the slab may be overwritten once these MMAs have read it (PAIR: in both CTAs)
+          if (PAIR) gemm_commit_pair(empty_bar + 8 * s); else gemm_commit(empty_bar + 8 * s);
         }
-        gemm_commit(tfull_bar + 8 * b);      // accumulators of this tile complete
+        // accumulators of this tile complete
+        if (PAIR) gemm_commit_pair(tfull_bar + 8 * b); else gemm_commit(tfull_bar + 8 * b);
       }
     }
     __syncwarp();
@@ -240,12 +296,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     const int r = q * 32 + lane;             // row of the tile this thread converts
     const bool leader = ew == 0 && lane == 0;
     uint32_t tc = 0, chunk_count = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+    for (int tile = (PAIR ? blockIdx.x >> 1 : blockIdx.x); tile < P.total_tiles; tile += (PAIR ? gridDim.x >> 1 : gridDim.x), ++tc) {
       const GemmProblemDev &pr = P.p[gemm_problem_of(P, tile)];
       const int local = tile - pr.tile_begin;
       const int m = local / pr.n_tiles, n = local - m * pr.n_tiles;
-      const int plane = n / pr.tiles_per_plane;
-      const int col0 = (n - plane * pr.tiles_per_plane) * pr.bn;     // first column of the tile within its plane
+      // column tiles run over the stacked product (all planes side by side)
+      const int gcol0 = n * pr.bn;                                   // first column of the tile in the stacked product
+      const int plane0 = gcol0 / pr.plane_cols;
+      const int col0 = gcol0 - plane0 * pr.plane_cols;               // ... and within its plane
       const uint32_t b = P.acc_bufs == 2 ? (tc & 1) : 0, ub = P.acc_bufs == 2 ? (tc >> 1) : tc;
       gemm_bar_wait(tfull_bar + 8 * b, ub & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,13 +336,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
           __syncwarp();
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (leader) {
-            if (m * kBM < pr.M) gemm_tma_store_3d(&pr.cf32, v * 32, m * kBM, 0, buf);
+            if ((PAIR ? 2 * m + (int)rank : m) * kBM < pr.M) gemm_tma_store_3d(&pr.cf32, v * 32, (PAIR ? 2 * m + (int)rank : m) * kBM, 0, buf);
             bulk_commit();
           }
           continue;
         }
         const int hh = MH == 2 ? (hc >= nchunks ? 1 : 0) : 0, cc = hc - hh * nchunks;   // row half, 64-column chunk
-        const int row0 = (m * MH + hh) * kBM;
+        const int row0 = PAIR ? (2 * m + (int)rank) * kBM : (m * MH + hh) * kBM;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + b * 256 + hh * P.acc_hstride;
         const int width = pr.bn - cc * 64 >= 64 ? 64 : 32;          // bn is a multiple of 32
         if (h * 32 < width) {
@@ -321,11 +379,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
         __syncwarp();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
-          if (col0 + cc * 64 < pr.plane_cols && row0 < pr.M) {
+          if (gcol0 + cc * 64 < pr.N && row0 < pr.M) {
+            // a tile may straddle two planes; each of its 64-column chunks lies in ONE of them (the host picks bn so)
+            int plane = plane0, pcol = col0 + cc * 64;
+            if (pcol >= pr.plane_cols) { pcol -= pr.plane_cols; ++plane; }
             if (P.n_peers > 0) {    // the same staging tile goes to every rank's buffer: GEMM and all-gather in one kernel
-              for (int pe = 0; pe < P.n_peers; ++pe) gemm_tma_store_3d(&P.peer_c[pe], col0 + cc * 64, row0, plane, buf);
+              for (int pe = 0; pe < P.n_peers; ++pe) gemm_tma_store_3d(&P.peer_c[pe], pcol, row0, plane, buf);
             } else {
-              gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, col0 + cc * 64, row0, plane, buf);
+              gemm_tma_store_3d(width == 64 ? &pr.c : &pr.c32, pcol, row0, plane, buf);
             }
           }
           // ONE group per chunk, also for a chunk that lies outside the output (empty group): the wait above counts
@@ -337,15 +398,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) gemm_bar_arrive(tempty_bar + 8 * b);    // this warp's reads of the buffer are done
+      if (lane == 0) {    // this warp's reads of the buffer are done (PAIR: the leader's MMA thread counts both CTAs' warps)
+        if (PAIR) gemm_bar_arrive_cluster(gemm_leader_addr(tempty_bar + 8 * b)); else gemm_bar_arrive(tempty_bar + 8 * b);
+      }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) gemm_cluster_sync(); else __syncthreads();   // PAIR: neither CTA leaves while the other may still signal it
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -375,11 +439,17 @@ static int gemm_bn_cap() {   // tuning: ACTK_GEMM_BN_MAX=128|192|256 caps the co
   return (v >= 64 && v <= 256) ? v / 32 * 32 : 256;
 }
 
-static int gemm_pick_bn(int N, int plane_cols, int step = 32) {
-  const int span = plane_cols;                         // tiles are laid out per plane
+static int gemm_pick_bn(int N, int plane_cols, int k_slabs, int step = 32) {
+  // Column tiles run over the stacked product.  Every 64-column chunk of a tile must lie in one plane: either tiles do not
+  // straddle planes (bn divides plane_cols), or planes are multiples of 64 columns at least one tile wide and tiles begin
+  // at multiples of 64 (a tile then straddles at most two planes).  The second form only for products with several K slabs
+  // per tile: in_proj at d_model 320 (two planes of 640 columns) takes 256- instead of 160-column tiles, 140 -> 116 us.
+  const int span = N;
+  const bool free_planes = plane_cols != N && plane_cols % 64 == 0 && plane_cols >= 256 && k_slabs >= 2;
+  if (free_planes && step < 64) step = 64;
   int best = step, best_tiles = 1 << 30, best_pad = 1 << 30;
   for (int bn = gemm_bn_cap() / step * step; bn >= step; bn -= step) {
-    if (plane_cols != N && span % bn != 0) continue;
+    if (plane_cols != N && !free_planes && plane_cols % bn != 0) continue;
     const int tiles = (span + bn - 1) / bn, pad = tiles * bn - span;
     if (tiles < best_tiles || (tiles == best_tiles && pad < best_pad)) { best = bn; best_tiles = tiles; best_pad = pad; }
   }
@@ -419,7 +489,7 @@ static int gemm_forced_mh() {
   return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 
-template <typename T, int MH>
+template <typename T, int MH, bool PAIR>
 static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms, int smem_max, int dev, cudaStream_t stream) {
   GemmEncodeFn fn = gemm_encode_fn();
   if (!fn) ACTK_FAIL(ACTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from this driver");
@@ -431,19 +501,19 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
   for (int g = 0; g < n; ++g)
     if (pr[g].epilogue == ACTK_GEMM_EPI_SILU) epilogue = ACTK_GEMM_EPI_SILU;
   P.epilogue = epilogue;
-  constexpr int kRows = MH * kBM;          // rows per tile
+  static_assert(!PAIR || MH == 1, "a CTA pair works on 2 x 128 rows");
+  constexpr int kRows = (PAIR ? 2 : MH) * kBM;          // rows per tile (PAIR: 128 per CTA)
   int tiles = 0, bn_max = 32;
   for (int g = 0; g < n; ++g) {
     const actk_gemm_problem &p = pr[g];
     GemmProblemDev &d = P.p[g];
     const int pc = p.N / p.planes;
-    d.bn = gemm_pick_bn(p.N, pc, p.n_peers > 0 ? 64 : 32);
+    d.bn = gemm_pick_bn(p.N, pc, (p.K + kBK - 1) / kBK, p.n_peers > 0 ? 64 : 32);
     d.plane_cols = pc;
     d.M = p.M; d.N = p.N;
     d.epilogue = p.epilogue;
     d.k_slabs = (p.K + kBK - 1) / kBK;
-    d.tiles_per_plane = (pc + d.bn - 1) / d.bn;
-    d.n_tiles = p.planes * d.tiles_per_plane;
+    d.n_tiles = (p.N + d.bn - 1) / d.bn;
     d.tile_begin = tiles;
     tiles += ((p.M + kRows - 1) / kRows) * d.n_tiles;
     bn_max = d.bn > bn_max ? d.bn : bn_max;
@@ -451,7 +521,7 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
     {   // A (K, M): slabs of 64 columns x (MH * 128) rows
       cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
       cuuint64_t strides[1] = {(cuuint64_t)p.lda * sizeof(T)};
-      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kRows};
+      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(MH * kBM)};
       CUresult r = fn(&d.a, dt, 2, const_cast<void *>(p.a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (A of problem %d) failed with CUresult %d", g, (int)r);
@@ -459,7 +529,7 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
     {   // W (K, N): slabs of 64 x bn; with planes the tile (plane, j) covers rows plane*pc + j*bn of the stacked weight
       cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
       cuuint64_t strides[1] = {(cuuint64_t)p.ldw * sizeof(T)};
-      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)d.bn};
+      cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(PAIR ? d.bn / 2 : d.bn)};      // PAIR: each CTA fetches half the rows
       CUresult r = fn(&d.w, dt, 2, const_cast<void *>(p.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) ACTK_FAIL(ACTK_ERR_CUDA, "gemm_tn: cuTensorMapEncodeTiled (W of problem %d) failed with CUresult %d", g, (int)r);
@@ -499,7 +569,7 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
     }
   }
   P.total_tiles = tiles;
-  P.stage_bytes = MH * kABytes + (uint32_t)bn_max * (kBK * 2);
+  P.stage_bytes = MH * kABytes + (uint32_t)(PAIR ? bn_max / 2 : bn_max) * (kBK * 2);
   // tensor memory: 512 columns.  Two accumulator buffers when a tile's accumulators fit in 256 columns, else one.
   if (MH == 1) { P.acc_bufs = 2; P.acc_hstride = 0; }
   else if (bn_max <= 128) { P.acc_bufs = 2; P.acc_hstride = 128; }
@@ -528,15 +598,31 @@ static int launch_gemm_mh(const actk_gemm_problem *pr, int n, int dtype, int sms
   const size_t smem = 1024 + (size_t)stages * P.stage_bytes + (size_t)P.epi_bufs * kEpiBufBytes + 16 * (size_t)stages + 64;
   bool f32side = false;
   for (int g = 0; g < n; ++g) f32side = f32side || P.p[g].f32_cols != 0;
-  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, false> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, false>;
-  if (f32side) kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, true> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, true>;
+  auto kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, false, PAIR> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, false, PAIR>;
+  if (f32side) kern = epilogue == ACTK_GEMM_EPI_SILU ? gemm_tn_kernel<T, ACTK_GEMM_EPI_SILU, MH, true, PAIR> : gemm_tn_kernel<T, ACTK_GEMM_EPI_NONE, MH, true, PAIR>;
   static int configured[64][4] = {};   // per device and kernel variant: dynamic shared memory limit raised
   const int ei = (epilogue == ACTK_GEMM_EPI_SILU ? 1 : 0) + (f32side ? 2 : 0);
   if (dev < 64 && !configured[dev][ei]) {
     ACTK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     configured[dev][ei] = 1;
   }
-  kern<<<tiles < sms ? tiles : sms, kGemmThreads, smem, stream>>>(P);
+  if (PAIR) {   // clusters of two CTAs (one TPC): one pair per 256-row tile
+    const int pairs = sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ACTK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P));
+  } else {
+    kern<<<tiles < sms ? tiles : sms, kGemmThreads, smem, stream>>>(P);
+  }
   ACTK_CUDA_OK(cudaGetLastError());
   return ACTK_OK;
 }
@@ -552,9 +638,22 @@ static int launch_gemm(const actk_gemm_problem *pr, int n, int dtype, cudaStream
   // 128 -> 171 us (one accumulator buffer: the epilogue no longer hides under the next tile's MMAs).  What bounds the
   // K >= 320 products is the MMAs' own operand reads from shared memory (12 KB per M128 N256 K16 instruction), which a taller
   // tile does not change.
-  int mh = 1;
-  return mh == 2 ? launch_gemm_mh<T, 2>(pr, n, dtype, sms, smem_max, dev, stream)
-                 : launch_gemm_mh<T, 1>(pr, n, dtype, sms, smem_max, dev, stream);
+  // CTA pairs (cta_group::2: clusters of two, every W byte fetched from L2 once per 256 rows) are opt-in (ACTK_GEMM_PAIR=1):
+  // built to cut the L2 -> SM traffic of the K >= 320 products by 30-45 %, parity-green and bit-identical, and measured SLOWER
+  // on B200 at config 2 (tools/bench_gemm_tn.py, us, single / pair): in_proj 115-126 / 150-172, dt_proj 144 / 202, out_proj
+  // 70.5 / 72.7, x_proj 76.7 / 80.0; only x_proj at d_model 1280 gains (54.7 -> 50.2).  A pair advances at the pace of its
+  // slower CTA at every ring slot and every accumulator hand-over, and these launches are not short of L2 bandwidth.
+  bool pair = false;
+  if (const char *e = getenv("ACTK_GEMM_PAIR")) {
+    if (e[0] == '1') {
+      pair = true;
+      for (int g = 0; g < n; ++g) if (pr[g].n_peers > 0) pair = false;     // the fused all-gather keeps single CTAs
+    }
+  }
+  if (pair) return launch_gemm_mh<T, 1, true>(pr, n, dtype, sms, smem_max, dev, stream);
+  const int mh = gemm_forced_mh() == 2 ? 2 : 1;
+  return mh == 2 ? launch_gemm_mh<T, 2, false>(pr, n, dtype, sms, smem_max, dev, stream)
+                 : launch_gemm_mh<T, 1, false>(pr, n, dtype, sms, smem_max, dev, stream);
 }
 
 }  // namespace actk

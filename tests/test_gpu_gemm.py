@@ -45,14 +45,18 @@ SHAPES = [
 ]
 
 
-@pytest.fixture(params=["auto", "1", "2"])
+@pytest.fixture(params=["auto", "pair", "rows256"])
 def tile_rows(request, monkeypatch):
-    """Both tile heights of the kernel (128-row tiles with two accumulator buffers, 256-row tiles that share every W slab
-    between two MMAs) on every shape, whatever the size heuristic would pick."""
-    if request.param != "auto":
-        monkeypatch.setenv("ACTK_GEMM_MH", request.param)
-    else:
-        monkeypatch.delenv("ACTK_GEMM_MH", raising=False)
+    """All launch forms of the kernel on every shape: the default (one CTA per 128-row tile, two accumulator buffers), and the
+    two opt-in forms that were built to share W slabs between more rows and measured slower — CTA pairs on 256-row tiles
+    (ACTK_GEMM_PAIR=1, cta_group::2: clusters of two, each CTA loads its 128 rows of A and half of every W slab, the leader
+    issues M = 256 MMAs) and 256-row tiles in one CTA (ACTK_GEMM_MH=2: every W slab feeds two M = 128 MMAs)."""
+    monkeypatch.delenv("ACTK_GEMM_PAIR", raising=False)
+    monkeypatch.delenv("ACTK_GEMM_MH", raising=False)
+    if request.param == "pair":
+        monkeypatch.setenv("ACTK_GEMM_PAIR", "1")
+    elif request.param == "rows256":
+        monkeypatch.setenv("ACTK_GEMM_MH", "2")
     return request.param
 
 
@@ -87,6 +91,14 @@ def test_gemm_silu_epilogue_planes_and_strided_operands(dtype, tile_rows):
     want = _ref(a.cpu(), w2.cpu(), dtype)
     _check(planes[0].cpu(), want[:, :192], dtype, "plane 0")
     _check(planes[1].cpu(), want[:, 192:], dtype, "plane 1")
+    # (2b) planes of 640 columns (in_proj at d_model 320): 256-column tiles, the third one straddles the two planes and
+    # its 64-column chunks go to different tensors
+    w3 = (torch.randn(2 * 640, 128, generator=g) / 11.0).to(dtype).cuda()
+    planes = torch.full((2, 700, 640), float("nan"), dtype=dtype, device="cuda")
+    gemm.run([gemm.Problem(a, w3, planes, planes=2)])
+    want = _ref(a.cpu(), w3.cpu(), dtype)
+    _check(planes[0].cpu(), want[:, :640], dtype, "plane 0 of 2 x 640")
+    _check(planes[1].cpu(), want[:, 640:], dtype, "plane 1 of 2 x 640")
     # (3) strided A (the dt columns of x_dbl read in place) and strided C (one token slot of the tail buffer)
     xdbl = torch.randn(500, 128, generator=g).to(dtype).cuda()
     wd = (torch.randn(256, 64, generator=g) / 8.0).to(dtype).cuda()
